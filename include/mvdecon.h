@@ -1,0 +1,144 @@
+/*
+ * mvdecon.h -- C ABI of the B200-native multi-view deconvolution path.
+ *
+ * This is the drop-in boundary for ONE hot path of PreibischLab/multiview-reconstruction: the block-wise multi-view
+ * Richardson-Lucy / efficient-Bayesian deconvolution loop (net.preibisch.mvrecon.process.deconvolution).
+ * Plain C linkage, plain pointers and sizes, no C++/torch types.  Reference citations use
+ *     M/ = src/main/java/net/preibisch/mvrecon/      U/ = src/main/java/util/
+ *
+ * Three levels:
+ *   L1  the symbols the UNMODIFIED reference binds through JNA today (CUDAFourierConvolution / CUDAStandardFunctions)
+ *   L2  ComputeBlockSeqThread.runIteration on one block (operator boundary)
+ *   L3  resident multi-view deconvolution: views, weights, PSF spectra and psi stay in HBM across iterations
+ *
+ * All volumes are dense float32, x fastest, then y, then z (ImgLib2 ArrayImg order, M/process/cuda/Block.java:299-308).
+ * Unless a function says "dims_zyx", dimension triples are in the reference's (x, y, z) order.
+ * Every L2/L3 function returns 0 on success; on failure a message is available from mvd_last_error().
+ * There is no CPU fallback: every entry point fails if no CUDA device is usable.
+ */
+#ifndef MVDECON_H
+#define MVDECON_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define MVD_API __declspec(dllexport)
+#else
+#define MVD_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * L1 -- legacy JNA boundary (replaces the external FourierConvolutionCUDALib).
+ * Java declarations: M/process/cuda/CUDAFourierConvolution.java:26-33, M/process/cuda/CUDAStandardFunctions.java:27-46.
+ * Loaded by NativeLibraryTools.loadNativeLibrary (M/process/cuda/NativeLibraryTools.java:84-153), called concurrently from
+ * one Java thread per device (M/process/deconvolution/MultiViewDeconvolutionSeq.java:92-150) via
+ * ComputeBlockSeqThreadCUDA.convolve1/2 (M/process/deconvolution/iteration/sequential/ComputeBlockSeqThreadCUDA.java:171-208).
+ *
+ * Semantics: circular convolution at the image size; the kernel is zero padded and its centre sample floor(k/2) is moved to
+ * the origin; imDim / kernelDim are {z, y, x} (CUDATools.getCUDACoordinates, M/process/cuda/CUDATools.java:41-49), data x
+ * fastest.  The callee never retains the pointers.  No error return (void, as declared by the reference): failures are
+ * reported on stderr and leave `im` untouched.  Image dimensions must be supported FFT lengths (every power of two from 32 to
+ * 1024 is; the reference GUI enforces powers of two, M/fiji/plugin/fusion/DeconvolutionGUI.java:674-678).
+ * ------------------------------------------------------------------------------------------------------------------ */
+MVD_API void convolution3DfftCUDAInPlace(float* im, int* imDim, float* kernel, int* kernelDim, int devCUDA);
+MVD_API float* convolution3DfftCUDA(float* im, int* imDim, float* kernel, int* kernelDim, int devCUDA); /* malloc'ed result */
+MVD_API int getCUDAcomputeCapabilityMinorVersion(int devCUDA);
+MVD_API int getCUDAcomputeCapabilityMajorVersion(int devCUDA);
+MVD_API int getNumDevicesCUDA(void);                         /* -1: driver/runtime failure (CUDAStandardFunctions.java:39-42) */
+MVD_API void getNameDeviceCUDA(int devCUDA, char* name);     /* caller buffer of 256 bytes (CUDATools.java:96-100)           */
+MVD_API long long getMemDeviceCUDA(int devCUDA);
+MVD_API long long getFreeMemDeviceCUDA(int devCUDA);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * L3 -- resident deconvolution context.
+ * Replaces MultiViewDeconvolution / MultiViewDeconvolutionSeq (M/process/deconvolution/MultiViewDeconvolution.java:90-200,
+ * MultiViewDeconvolutionSeq.java:58-180), DeconView / DeconViews / DeconViewPSF (DeconView.java:118-184, DeconViews.java:44-81,
+ * DeconViewPSF.java:119-254) and the Block machinery (M/process/cuda/Block*.java) for this path.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct mvd_context mvd_context;
+
+/* DeconViewPSF.PSFTYPE ordinals (DeconViewPSF.java:52) */
+enum { MVD_PSF_OPTIMIZATION_II = 0, MVD_PSF_OPTIMIZATION_I = 1, MVD_PSF_EFFICIENT_BAYESIAN = 2, MVD_PSF_INDEPENDENT = 3 };
+/* out-of-bounds strategies of mvd_convolve */
+enum { MVD_EXT_MIRROR = 0, MVD_EXT_ZERO = 1, MVD_EXT_CONST = 2 };
+
+typedef struct mvd_config {
+    int device;          /* CUDA device ordinal                                                                         */
+    int dims[3];         /* size of the fused / deconvolved volume psi (x,y,z)  -- views.getPSIDimensions()             */
+    int num_views;       /* number of (virtual) views                                                                   */
+    int psf_type;        /* MVD_PSF_*                                                                                   */
+    float lambda;        /* Tikhonov parameter, 0 = off (ComputeBlockSeqThreadCPU.lambda)                               */
+    float min_value;     /* MultiViewDeconvolution.minValue = 1e-4f (MultiViewDeconvolution.java:50)                    */
+    /* z-slab sharding across processes/GPUs.  Unsharded: shard_lo = 0, shard_hi = dims[2], local_z0 = 0, local_nz = dims[2].
+     * Sharded: this context owns planes [shard_lo, shard_hi) and its arrays hold planes [local_z0, local_z0 + local_nz),
+     * which must include the halo mvd_halo_planes() reports on interior sides.                                          */
+    int shard_lo, shard_hi;
+    int local_z0, local_nz;
+    int max_fft_len;     /* 0 = default (1152); caps the FFT tile edge                                                  */
+} mvd_config;
+
+MVD_API const char* mvd_last_error(void);                     /* thread-local message of the last failing call          */
+MVD_API int mvd_version(void);
+
+MVD_API int mvd_create(const mvd_config* cfg, mvd_context** out);
+MVD_API int mvd_destroy(mvd_context* ctx);
+
+/* DeconView: observed image (0 where the view has no data, MultiViewDeconvolution.outsideValueImg) and weight volume of
+ * view v; local array size dims[0]*dims[1]*local_nz.  _host copies host->device, _device borrows caller-owned device
+ * memory that must stay valid until mvd_destroy.                                                                       */
+MVD_API int mvd_set_view(mvd_context* ctx, int v, const float* img_host, const float* weight_host);
+MVD_API int mvd_set_view_device(mvd_context* ctx, int v, const float* img_dev, const float* weight_dev);
+/* DeconViewPSF( kernel, psfType ): raw PSF of view v (need not be normalised), size kdims (x,y,z), odd sizes expected.  */
+MVD_API int mvd_set_psf(mvd_context* ctx, int v, const float* psf, const int kdims[3]);
+/* alternative: hand over kernel1 / kernel2 directly (what runIteration receives, ComputeBlockSeqThread.java:54-61)      */
+MVD_API int mvd_set_kernels(mvd_context* ctx, int v, const float* k1, const int k1dims[3], const float* k2, const int k2dims[3]);
+/* new DeconViews(...): derives kernel1/kernel2 by PSFTYPE in list order, plans the FFT tiles, builds and keeps all
+ * kernel spectra resident in HBM (replaces the lazy DeconViewPSF.getKernel{1,2}FFT, DeconViewPSF.java:79-111).          */
+MVD_API int mvd_init_views(mvd_context* ctx);
+MVD_API int mvd_get_kernel_dims(mvd_context* ctx, int v, int which /*1|2*/, int kdims[3]);
+MVD_API int mvd_get_kernel(mvd_context* ctx, int v, int which /*1|2*/, float* out);
+
+/* psi and the per-view max intensities (what PsiInit hands to the loop, MultiViewDeconvolution.java:115-135)            */
+MVD_API int mvd_set_psi(mvd_context* ctx, const float* psi_host);
+MVD_API int mvd_get_psi(mvd_context* ctx, float* psi_host);
+MVD_API int mvd_set_max_intensities(mvd_context* ctx, const float* max_per_view);
+
+/* One view update of MultiViewDeconvolutionSeq.runNextIteration (:69-176): psi <- update(psi, view v).
+ * stats (may be NULL) receives {sumChange, maxChange} over the owned voxels (IterationStatistics, ComputeBlockThread.java:64-68). */
+MVD_API int mvd_run_view_update(mvd_context* ctx, int v, double stats[2]);
+/* MultiViewDeconvolution.runIterations for n iterations; stats (may be NULL) receives n*num_views pairs.                */
+MVD_API int mvd_run_iterations(mvd_context* ctx, int n, double* stats);
+/* Asynchronous variant + explicit synchronisation (lets a multi-GPU host overlap its halo exchange).                    */
+MVD_API int mvd_enqueue_view_update(mvd_context* ctx, int v);
+MVD_API int mvd_synchronize(mvd_context* ctx);
+MVD_API int mvd_fetch_stats(mvd_context* ctx, int count, double* stats);
+
+/* Introspection for benchmarks / multi-GPU hosts */
+MVD_API int mvd_tile_info(mvd_context* ctx, int tile_dims[3], int* num_tiles, double* fft_volume_ratio, int* launches_per_view_update);
+MVD_API int mvd_halo_planes(mvd_context* ctx, int* lo, int* hi);            /* z planes needed beyond the owned slab       */
+MVD_API int mvd_psi_device_ptr(mvd_context* ctx, void** current);           /* device address of the current psi buffer    */
+MVD_API int mvd_stream_handle(mvd_context* ctx, void** cuda_stream);
+
+/* Generic FFT convolution of a host volume with a host kernel on the device (used by the PSF derivation; exported for
+ * tests and callers that need U/FFTConvolution.convolve semantics, U/FFTConvolution.java:490-603): out has the size of img,
+ * kernel centre floor(k/2), img extended by `ext`.                                                                      */
+MVD_API int mvd_convolve(int device, const float* img, const int dims[3], const float* kernel, const int kdims[3], int ext,
+                         float ext_value, float* out);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * L2 -- ComputeBlockSeqThread.runIteration on ONE halo'd block held in host memory
+ * (M/process/deconvolution/iteration/sequential/ComputeBlockSeqThread.java:54-61; CPU variant ComputeBlockSeqThreadCPU.java:79-169).
+ * psi_block is read and overwritten (it is the worker's psiBlockTmp), img_block / weight_block are the zero-extended block
+ * cut-outs, block_dims (x,y,z).  conv1 extends the block by mirroring, conv2 by the constant 1 exactly like the CPU thread.
+ * stats receives {sumChange, maxChange} over the whole block (as the reference does).
+ * ------------------------------------------------------------------------------------------------------------------ */
+MVD_API int mvd_block_iteration(int device, float* psi_block, const float* img_block, const float* weight_block,
+                                const int block_dims[3], const float* kernel1, const int k1dims[3], const float* kernel2,
+                                const int k2dims[3], float lambda, float min_value, float max_intensity, double stats[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVDECON_H */

@@ -1,0 +1,535 @@
+"""
+multiview-reconstruction_b200 -- B200-native drop-in for ONE hot path of PreibischLab/multiview-reconstruction:
+the block-wise multi-view Richardson-Lucy / efficient-Bayesian deconvolution loop
+(net.preibisch.mvrecon.process.deconvolution).
+
+This package is a thin ctypes binding of the C ABI in ``include/mvdecon.h`` (``libmvdecon.so``, hand-written
+sm_100a kernels) plus a host-side mirror of the reference's operator interface for this path so that
+callers -- and the parity tests -- read like the reference's own call sequence
+(``M/headless/deconvolution/TestDeconvolution.java:103-254``):
+
+    views = DeconViews([DeconView(img, weight, psf, PSFTYPE.EFFICIENT_BAYESIAN) ...])
+    decon = MultiViewDeconvolutionSeq(views, num_iterations, psi_init, lambda_=0.006)
+    decon.runIterations(); psi = decon.getPSI()
+
+There is NO CPU fallback: importing works anywhere, but every compute entry point raises if the CUDA
+library is missing or no device is usable.  (The directory name contains a hyphen; import it through the
+``mvrecon_b200`` shim at the repository root.)
+
+Array convention: numpy arrays indexed [z, y, x] (x fastest) == the reference's ArrayImg order.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBRARY_PATH = os.path.join(_HERE, "libmvdecon.so")
+
+# MultiViewDeconvolution constants (M/process/deconvolution/MultiViewDeconvolution.java:48-50)
+outsideValueImg = 0.0
+minValueImg = 1.0
+minValue = 0.0001
+
+
+class PSFTYPE(enum.IntEnum):
+    """DeconViewPSF.PSFTYPE ordinals (M/process/deconvolution/DeconViewPSF.java:52)."""
+    OPTIMIZATION_II = 0
+    OPTIMIZATION_I = 1
+    EFFICIENT_BAYESIAN = 2
+    INDEPENDENT = 3
+
+
+class MvdError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("dims", C.c_int * 3), ("num_views", C.c_int), ("psf_type", C.c_int),
+                ("lambda_", C.c_float), ("min_value", C.c_float), ("shard_lo", C.c_int), ("shard_hi", C.c_int),
+                ("local_z0", C.c_int), ("local_nz", C.c_int), ("max_fft_len", C.c_int)]
+
+
+_F = C.POINTER(C.c_float)
+_I = C.POINTER(C.c_int)
+_D = C.POINTER(C.c_double)
+
+# every symbol include/mvdecon.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "convolution3DfftCUDAInPlace": (None, [_F, _I, _F, _I, C.c_int]),
+    "convolution3DfftCUDA": (C.c_void_p, [_F, _I, _F, _I, C.c_int]),
+    "getCUDAcomputeCapabilityMinorVersion": (C.c_int, [C.c_int]),
+    "getCUDAcomputeCapabilityMajorVersion": (C.c_int, [C.c_int]),
+    "getNumDevicesCUDA": (C.c_int, []),
+    "getNameDeviceCUDA": (None, [C.c_int, C.c_char_p]),
+    "getMemDeviceCUDA": (C.c_longlong, [C.c_int]),
+    "getFreeMemDeviceCUDA": (C.c_longlong, [C.c_int]),
+    "mvd_last_error": (C.c_char_p, []),
+    "mvd_version": (C.c_int, []),
+    "mvd_create": (C.c_int, [C.POINTER(_Config), C.POINTER(C.c_void_p)]),
+    "mvd_destroy": (C.c_int, [C.c_void_p]),
+    "mvd_set_view": (C.c_int, [C.c_void_p, C.c_int, _F, _F]),
+    "mvd_set_view_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mvd_set_psf": (C.c_int, [C.c_void_p, C.c_int, _F, _I]),
+    "mvd_set_kernels": (C.c_int, [C.c_void_p, C.c_int, _F, _I, _F, _I]),
+    "mvd_init_views": (C.c_int, [C.c_void_p]),
+    "mvd_get_kernel_dims": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _I]),
+    "mvd_get_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _F]),
+    "mvd_set_psi": (C.c_int, [C.c_void_p, _F]),
+    "mvd_get_psi": (C.c_int, [C.c_void_p, _F]),
+    "mvd_set_max_intensities": (C.c_int, [C.c_void_p, _F]),
+    "mvd_run_view_update": (C.c_int, [C.c_void_p, C.c_int, _D]),
+    "mvd_run_iterations": (C.c_int, [C.c_void_p, C.c_int, _D]),
+    "mvd_enqueue_view_update": (C.c_int, [C.c_void_p, C.c_int]),
+    "mvd_synchronize": (C.c_int, [C.c_void_p]),
+    "mvd_fetch_stats": (C.c_int, [C.c_void_p, C.c_int, _D]),
+    "mvd_tile_info": (C.c_int, [C.c_void_p, _I, _I, _D, _I]),
+    "mvd_halo_planes": (C.c_int, [C.c_void_p, _I, _I]),
+    "mvd_psi_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mvd_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mvd_convolve": (C.c_int, [C.c_int, _F, _I, _F, _I, C.c_int, C.c_float, _F]),
+    "mvd_block_iteration": (C.c_int, [C.c_int, _F, _F, _F, _I, _F, _I, _F, _I, C.c_float, C.c_float, C.c_float, _D]),
+}
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(_F)
+
+
+def _i3(xyz: Sequence[int]):
+    return (C.c_int * 3)(int(xyz[0]), int(xyz[1]), int(xyz[2]))
+
+
+def _xyz(a: np.ndarray) -> Tuple[int, int, int]:
+    return (a.shape[2], a.shape[1], a.shape[0])
+
+
+class Lib:
+    """The loaded C-ABI library."""
+
+    def __init__(self, path: str = LIBRARY_PATH):
+        if not os.path.exists(path):
+            raise MvdError(f"{path} is missing: build it with `make` (nvcc, sm_100a). There is no CPU fallback.")
+        self.path = path
+        self.dll = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(self.dll, name)          # AttributeError if a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise MvdError(self.dll.mvd_last_error().decode("utf-8", "replace"))
+
+    # ---- L1: legacy JNA surface (M/process/cuda/CUDAFourierConvolution.java:26-33) -------------------------------
+    def convolution3DfftCUDAInPlace(self, im: np.ndarray, kernel: np.ndarray, devCUDA: int = 0) -> None:
+        """im [z,y,x] float32 contiguous is overwritten by the circular convolution with `kernel` [z,y,x]."""
+        assert im.dtype == np.float32 and im.flags.c_contiguous
+        k = _f32(kernel)
+        imdim = (C.c_int * 3)(*im.shape)          # {z,y,x}, CUDATools.getCUDACoordinates (CUDATools.java:41-49)
+        kdim = (C.c_int * 3)(*k.shape)
+        self.dll.convolution3DfftCUDAInPlace(_fp(im), imdim, _fp(k), kdim, int(devCUDA))
+
+    def getNumDevicesCUDA(self) -> int:
+        return int(self.dll.getNumDevicesCUDA())
+
+    def getNameDeviceCUDA(self, dev: int) -> str:
+        buf = C.create_string_buffer(256)
+        self.dll.getNameDeviceCUDA(int(dev), buf)
+        return buf.value.decode("utf-8", "replace")
+
+    # ---- generic convolution (U/FFTConvolution.convolve semantics) ------------------------------------------------
+    def convolve(self, img: np.ndarray, kernel: np.ndarray, ext: str = "mirror", ext_value: float = 0.0, device: int = 0) -> np.ndarray:
+        img = _f32(img)
+        kernel = _f32(kernel)
+        out = np.empty_like(img)
+        mode = {"mirror": 0, "zero": 1, "const": 2}[ext]
+        self.check(self.dll.mvd_convolve(int(device), _fp(img), _i3(_xyz(img)), _fp(kernel), _i3(_xyz(kernel)), mode,
+                                         C.c_float(ext_value), _fp(out)))
+        return out
+
+    # ---- L2: ComputeBlockSeqThread.runIteration on one block ------------------------------------------------------
+    def block_iteration(self, psi_block: np.ndarray, img_block: np.ndarray, weight_block: np.ndarray, kernel1: np.ndarray,
+                        kernel2: np.ndarray, lambda_: float, min_value: float, max_intensity: float, device: int = 0):
+        assert psi_block.dtype == np.float32 and psi_block.flags.c_contiguous
+        ib, wb, k1, k2 = _f32(img_block), _f32(weight_block), _f32(kernel1), _f32(kernel2)
+        st = (C.c_double * 2)()
+        self.check(self.dll.mvd_block_iteration(int(device), _fp(psi_block), _fp(ib), _fp(wb), _i3(_xyz(psi_block)), _fp(k1),
+                                                _i3(_xyz(k1)), _fp(k2), _i3(_xyz(k2)), C.c_float(lambda_), C.c_float(min_value),
+                                                C.c_float(max_intensity), st))
+        return float(st[0]), float(st[1])
+
+
+_LIB: Optional[Lib] = None
+
+
+def lib() -> Lib:
+    """The product library (in-tree libmvdecon.so). Raises MvdError when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        _LIB = Lib(LIBRARY_PATH)
+    return _LIB
+
+
+# =====================================================================================================================
+# Host-side mirror of the reference's operator interface for this path
+# =====================================================================================================================
+class IterationStatistics:
+    """ComputeBlockThread.IterationStatistics (M/process/deconvolution/iteration/ComputeBlockThread.java:64-68)."""
+
+    def __init__(self, sumChange: float = 0.0, maxChange: float = -1.0):
+        self.sumChange = sumChange
+        self.maxChange = maxChange
+
+    def __repr__(self):
+        return f"IterationStatistics(sumChange={self.sumChange!r}, maxChange={self.maxChange!r})"
+
+
+class DeconViewPSF:
+    """M/process/deconvolution/DeconViewPSF.java: holds the raw PSF; kernel1/kernel2 exist after DeconViews init."""
+
+    def __init__(self, kernel: np.ndarray, psfType: PSFTYPE = PSFTYPE.INDEPENDENT):
+        self.psf = _f32(kernel)
+        self.psfType = PSFTYPE(psfType)
+        self._kernel1: Optional[np.ndarray] = None
+        self._kernel2: Optional[np.ndarray] = None
+
+    def getKernel1(self) -> np.ndarray:
+        if self._kernel1 is None:
+            raise MvdError("getKernel1 can only be called after DeconViews(...) initialised the PSFs")
+        return self._kernel1
+
+    def getKernel2(self) -> np.ndarray:
+        if self._kernel2 is None:
+            raise MvdError("getKernel2 can only be called after DeconViews(...) initialised the PSFs")
+        return self._kernel2
+
+
+class DeconView:
+    """M/process/deconvolution/DeconView.java:118-184 -- image, weight, PSF of one virtual view."""
+
+    def __init__(self, image: np.ndarray, weight: np.ndarray, kernel: np.ndarray, psfType: PSFTYPE = PSFTYPE.INDEPENDENT,
+                 title: Optional[str] = None):
+        self.image = _f32(image)
+        self.weight = _f32(weight)
+        if self.image.shape != self.weight.shape or self.image.ndim != 3:
+            raise MvdError("image and weight must be 3-d volumes of identical size")
+        self.psf = DeconViewPSF(kernel, psfType)
+        self.title = title
+
+    def getImage(self):
+        return self.image
+
+    def getWeight(self):
+        return self.weight
+
+    def getPSF(self) -> DeconViewPSF:
+        return self.psf
+
+
+class DeconViews:
+    """M/process/deconvolution/DeconViews.java:44-81 -- dimension check + PSF init in list order.
+    Owns the resident device context (the analogue of the ExecutorService the reference's DeconViews owns)."""
+
+    def __init__(self, views: Sequence[DeconView], device: int = 0, lambda_: float = 0.0, min_value: float = minValue,
+                 shard: Optional[Tuple[int, int, int, int]] = None, global_dims_zyx: Optional[Sequence[int]] = None,
+                 max_fft_len: int = 0, library: Optional[Lib] = None):
+        self.lib = library or lib()
+        self.views = list(views)
+        if not self.views:
+            raise MvdError("no views")
+        shp = self.views[0].image.shape
+        types = {v.psf.psfType for v in self.views}
+        if len(types) != 1:
+            raise MvdError("all views must use the same PSFTYPE")
+        for v in self.views:                                           # DeconViews.java:61-64
+            if v.image.shape != shp:
+                raise MvdError("dimensions of all views must be identical")
+        self.local_shape = shp
+        gz = shp if global_dims_zyx is None else tuple(int(x) for x in global_dims_zyx)
+        self.psi_dims_zyx = gz
+        cfg = _Config()
+        cfg.device = int(device)
+        cfg.dims[0], cfg.dims[1], cfg.dims[2] = gz[2], gz[1], gz[0]
+        cfg.num_views = len(self.views)
+        cfg.psf_type = int(self.views[0].psf.psfType)
+        cfg.lambda_ = float(lambda_)
+        cfg.min_value = float(min_value)
+        if shard is not None:
+            cfg.shard_lo, cfg.shard_hi, cfg.local_z0, cfg.local_nz = (int(x) for x in shard)
+        cfg.max_fft_len = int(max_fft_len)
+        self._ctx = C.c_void_p()
+        self.lib.check(self.lib.dll.mvd_create(C.byref(cfg), C.byref(self._ctx)))
+        try:
+            for i, v in enumerate(self.views):
+                self.lib.check(self.lib.dll.mvd_set_view(self._ctx, i, _fp(v.image), _fp(v.weight)))
+                self.lib.check(self.lib.dll.mvd_set_psf(self._ctx, i, _fp(v.psf.psf), _i3(_xyz(v.psf.psf))))
+            self.lib.check(self.lib.dll.mvd_init_views(self._ctx))       # psf.init for every view + resident spectra
+            for i, v in enumerate(self.views):
+                for which in (1, 2):
+                    kd = (C.c_int * 3)()
+                    self.lib.check(self.lib.dll.mvd_get_kernel_dims(self._ctx, i, which, kd))
+                    k = np.empty((kd[2], kd[1], kd[0]), dtype=np.float32)
+                    self.lib.check(self.lib.dll.mvd_get_kernel(self._ctx, i, which, _fp(k)))
+                    if which == 1:
+                        v.psf._kernel1 = k
+                    else:
+                        v.psf._kernel2 = k
+        except Exception:
+            self.close()
+            raise
+
+    def getViews(self) -> List[DeconView]:
+        return self.views
+
+    def getPSIDimensions(self):
+        return self.psi_dims_zyx
+
+    def tile_info(self):
+        td = (C.c_int * 3)()
+        n = C.c_int()
+        r = C.c_double()
+        l = C.c_int()
+        self.lib.check(self.lib.dll.mvd_tile_info(self._ctx, td, C.byref(n), C.byref(r), C.byref(l)))
+        return {"tile_dims_xyz": (td[0], td[1], td[2]), "num_tiles": n.value, "fft_volume_ratio": r.value,
+                "launches_per_view_update": l.value}
+
+    def halo_planes(self):
+        lo, hi = C.c_int(), C.c_int()
+        self.lib.check(self.lib.dll.mvd_halo_planes(self._ctx, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.dll.mvd_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PsiInitFromRAI:
+    """PsiInitFromRAI semantics (M/process/deconvolution/init/PsiInitFromRAI.java:65-82): psi0 and the per-view maxima are
+    supplied as data."""
+
+    def __init__(self, psi0: np.ndarray, max_intensities: Sequence[float]):
+        self.psi0 = _f32(psi0)
+        self.max = np.asarray(max_intensities, dtype=np.float32)
+
+    def getMax(self):
+        return self.max
+
+
+class MultiViewDeconvolutionSeq:
+    """MultiViewDeconvolution + MultiViewDeconvolutionSeq (M/process/deconvolution/MultiViewDeconvolution.java:90-200,
+    MultiViewDeconvolutionSeq.java:58-180): OSEM loop, psi updated after every view, resident on the device."""
+
+    def __init__(self, views: DeconViews, numIterations: int, psiInit: PsiInitFromRAI):
+        self.views = views
+        self.numIterations = int(numIterations)
+        self.it = 0
+        self.lib = views.lib
+        self.max = np.asarray(psiInit.getMax(), dtype=np.float32)
+        if self.max.shape != (len(views.getViews()),):
+            raise MvdError("need one max intensity per view")
+        if psiInit.psi0.shape != views.local_shape:
+            raise MvdError("psi dimensions must equal the view dimensions")
+        self.lib.check(self.lib.dll.mvd_set_max_intensities(views._ctx, _fp(self.max)))
+        self.lib.check(self.lib.dll.mvd_set_psi(views._ctx, _fp(psiInit.psi0)))
+        self.stats: List[List[IterationStatistics]] = []
+
+    def initWasSuccessful(self) -> bool:
+        return self.max is not None
+
+    def runNextIteration(self) -> List[IterationStatistics]:
+        self.it += 1
+        out = []
+        for v in range(len(self.views.getViews())):
+            st = (C.c_double * 2)()
+            self.lib.check(self.lib.dll.mvd_run_view_update(self.views._ctx, v, st))
+            out.append(IterationStatistics(float(st[0]), float(st[1])))
+        self.stats.append(out)
+        return out
+
+    def runIterations(self) -> None:
+        n = self.numIterations - self.it
+        if n <= 0:
+            return
+        V = len(self.views.getViews())
+        st = (C.c_double * (2 * n * V))()
+        self.lib.check(self.lib.dll.mvd_run_iterations(self.views._ctx, n, st))
+        for i in range(n):
+            self.stats.append([IterationStatistics(float(st[2 * (i * V + v)]), float(st[2 * (i * V + v) + 1])) for v in range(V)])
+        self.it = self.numIterations
+
+    def getPSI(self) -> np.ndarray:
+        psi = np.empty(self.views.local_shape, dtype=np.float32)
+        self.lib.check(self.lib.dll.mvd_get_psi(self.views._ctx, _fp(psi)))
+        return psi
+
+
+class ComputeBlockSeqThreadB200:
+    """The L2 operator: ComputeBlockSeqThread.runIteration on one halo'd block
+    (M/process/deconvolution/iteration/sequential/ComputeBlockSeqThread.java:54-61)."""
+
+    def __init__(self, minValue_: float, lambda_: float, id_: int, blockSize_xyz: Sequence[int], device: int, library: Optional[Lib] = None):
+        self.lib = library or lib()
+        self.minValue = float(minValue_)
+        self.lambda_ = float(lambda_)
+        self.id = int(id_)
+        self.blockSize = tuple(int(b) for b in blockSize_xyz)
+        self.device = int(device)
+        self.psiBlockTmp = np.zeros(self.blockSize[::-1], dtype=np.float32)
+
+    def getPsiBlockTmp(self) -> np.ndarray:
+        return self.psiBlockTmp
+
+    def getBlockSize(self):
+        return self.blockSize
+
+    def getMinValue(self) -> float:
+        return self.minValue
+
+    def getId(self) -> int:
+        return self.id
+
+    def runIteration(self, view, block, imgBlock: np.ndarray, weightBlock: np.ndarray, maxIntensityView: float,
+                     kernel1: np.ndarray, kernel2: np.ndarray) -> IterationStatistics:
+        s, m = self.lib.block_iteration(self.psiBlockTmp, imgBlock, weightBlock, kernel1, kernel2, self.lambda_, self.minValue,
+                                        float(maxIntensityView), self.device)
+        return IterationStatistics(s, m)
+
+
+class ComputeBlockSeqThreadB200Factory:
+    """ComputeBlockThreadFactory (M/process/deconvolution/iteration/ComputeBlockThreadFactory.java:25-29); one worker per
+    device like ComputeBlockSeqThreadCUDAFactory (…/sequential/ComputeBlockSeqThreadCUDAFactory.java:41-64)."""
+
+    def __init__(self, minValue_: float, lambda_: float, blockSize_xyz: Sequence[int], devices: Sequence[int] = (0,), library: Optional[Lib] = None):
+        self.minValue, self.lambda_, self.blockSize, self.devices, self.library = minValue_, lambda_, tuple(blockSize_xyz), list(devices), library
+
+    def create(self, id_: int) -> ComputeBlockSeqThreadB200:
+        return ComputeBlockSeqThreadB200(self.minValue, self.lambda_, id_, self.blockSize, self.devices[id_], self.library)
+
+    def numParallelBlocks(self) -> int:
+        return len(self.devices)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Block geometry of the reference (host logic; used by the L2 drop-in driver below)
+# ---------------------------------------------------------------------------------------------------------------------
+class Block:
+    """M/process/cuda/Block.java -- (x,y,z) order like the reference."""
+
+    def __init__(self, blockSize, offset, effectiveSize, effectiveOffset, effectiveLocalOffset):
+        self.blockSize, self.offset, self.effectiveSize = tuple(blockSize), tuple(offset), tuple(effectiveSize)
+        self.effectiveOffset, self.effectiveLocalOffset = tuple(effectiveOffset), tuple(effectiveLocalOffset)
+
+    def min(self, d: int) -> int:
+        return self.offset[d]
+
+    def copyBlock(self, source: np.ndarray, mode: str = "reflect") -> np.ndarray:
+        """Block.copyBlock (Block.java:158-197): cut [offset, offset+blockSize) out of the extended source."""
+        bs, off, n = self.blockSize[::-1], self.offset[::-1], source.shape
+        lo = [max(0, -off[d]) for d in range(3)]
+        hi = [max(0, off[d] + bs[d] - n[d]) for d in range(3)]
+        p = np.pad(source, list(zip(lo, hi)), mode=mode) if mode == "reflect" else np.pad(source, list(zip(lo, hi)), mode="constant")
+        return np.ascontiguousarray(p[tuple(slice(off[d] + lo[d], off[d] + lo[d] + bs[d]) for d in range(3))])
+
+    def pasteBlock(self, target: np.ndarray, block: np.ndarray) -> None:
+        """Block.pasteBlock (Block.java:199-239): effective region only."""
+        es, eo, el = self.effectiveSize[::-1], self.effectiveOffset[::-1], self.effectiveLocalOffset[::-1]
+        target[tuple(slice(eo[d], eo[d] + es[d]) for d in range(3))] = block[tuple(slice(el[d], el[d] + es[d]) for d in range(3))]
+
+
+def divideIntoBlocks(imgSize_xyz, blockSize_xyz, kernelSize_xyz) -> Optional[List[Block]]:
+    """BlockGeneratorFixedSizePrecise.divideIntoBlocks (M/process/cuda/BlockGeneratorFixedSizePrecise.java:59-131)."""
+    n = len(imgSize_xyz)
+    eff = [blockSize_xyz[d] - kernelSize_xyz[d] + 1 for d in range(n)]
+    if min(eff) <= 0:
+        return None
+    loc = [kernelSize_xyz[d] // 2 for d in range(n)]
+    nb = [-(-imgSize_xyz[d] // eff[d]) for d in range(n)]
+    blocks = []
+    for bz in range(nb[2]):
+        for by in range(nb[1]):
+            for bx in range(nb[0]):
+                cur = (bx, by, bz)
+                eo = [cur[d] * eff[d] for d in range(n)]
+                es = [min(eff[d], imgSize_xyz[d] - eo[d]) for d in range(n)]
+                blocks.append(Block(blockSize_xyz, [eo[d] - loc[d] for d in range(n)], es, eo, loc))
+    return blocks
+
+
+def sortBlocksBySmallestFootprint(blocks: List[Block], psiDims_xyz, minRequiredBlocks: int = 1) -> List[List[Block]]:
+    """BlockSorter.sortBlocksBySmallestFootprint (M/process/cuda/BlockSorter.java:55-143)."""
+    n = len(psiDims_xyz)
+    eff = blocks[0].effectiveSize
+    nb = [-(-psiDims_xyz[d] // eff[d]) for d in range(n)]
+    size_to_dim, sizes = {}, []
+    for d in range(n):
+        s = 1
+        for e in range(n):
+            if e != d:
+                s *= nb[e]
+        sizes.append(s)
+        size_to_dim[s] = d
+    sizes.sort()
+    minDim = -1
+    for i in range(n):
+        if minDim == -1 and (sizes[i] >= minRequiredBlocks or i == n - 1):
+            minDim = size_to_dim[sizes[i]]
+    layers, total = [], 0
+    for i in range(nb[minDim]):
+        off = blocks[0].offset[minDim] + i * eff[minDim]
+        layer = [b for b in blocks if b.min(minDim) == off]
+        total += len(layer)
+        layers.append(layer)
+    return layers if total == len(blocks) else [list(blocks)]
+
+
+def runNextIterationBlocked(psi: np.ndarray, views: Sequence[DeconView], kernels: Sequence[Tuple[np.ndarray, np.ndarray]],
+                            max_intensities: Sequence[float], factory: ComputeBlockSeqThreadB200Factory) -> List[IterationStatistics]:
+    """MultiViewDeconvolutionSeq.runNextIteration driven through the L2 operator, block by block with the reference's
+    delayed write-back (MultiViewDeconvolutionSeq.java:69-176).  psi is updated in place."""
+    worker = factory.create(0)
+    out = []
+    for v, view in enumerate(views):
+        k1, k2 = kernels[v]
+        ksz = tuple(2 * k - 1 for k in k1.shape[::-1])                  # DeconView.java:155-157
+        blocks = divideIntoBlocks(psi.shape[::-1], factory.blockSize, ksz)
+        if blocks is None:
+            raise MvdError("block smaller than the kernel")
+        batches = sortBlocksBySmallestFootprint(blocks, psi.shape[::-1])
+        total = len(blocks)
+        st = IterationStatistics()
+        prev = []
+        for batch in batches:
+            cur = []
+            for blk in batch:
+                worker.psiBlockTmp[...] = blk.copyBlock(psi, "reflect")
+                s = worker.runIteration(view, blk, blk.copyBlock(view.image, "zero"), blk.copyBlock(view.weight, "zero"),
+                                        max_intensities[v], k1, k2)
+                st.sumChange += s.sumChange
+                st.maxChange = max(st.maxChange, s.maxChange)
+                if total == 1:
+                    blk.pasteBlock(psi, worker.psiBlockTmp)
+                else:
+                    cur.append((blk, worker.psiBlockTmp.copy()))
+            for blk, data in prev:
+                blk.pasteBlock(psi, data)
+            prev = cur
+        for blk, data in prev:
+            blk.pasteBlock(psi, data)
+        out.append(st)
+    return out

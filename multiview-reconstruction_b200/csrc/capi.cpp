@@ -1,0 +1,305 @@
+// extern "C" surface declared in include/mvdecon.h
+#include "../../include/mvdecon.h"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "engine.h"
+
+using namespace mvd;
+
+struct mvd_context {
+    Engine* engine = nullptr;
+    int halo_lo = 0, halo_hi = 0;
+};
+
+namespace {
+thread_local std::string g_last_error;
+
+template <class F>
+int guarded(F&& f) {
+    try {
+        f();
+        g_last_error.clear();
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return 1;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return 1;
+    }
+}
+void require(bool c, const char* msg) { if (!c) throw Error(msg); }
+
+#ifndef MVD_HOST_EMU
+void require_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) throw Error(std::string("no usable CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) throw Error("CUDA device ordinal out of range");
+}
+#else
+void require_device(int) {}
+#endif
+}  // namespace
+
+extern "C" {
+
+const char* mvd_last_error(void) { return g_last_error.c_str(); }
+int mvd_version(void) { return 100; }
+
+int mvd_create(const mvd_config* cfg, mvd_context** out) {
+    return guarded([&] {
+        require(cfg && out, "null argument");
+        require_device(cfg->device);
+        Engine::Config c;
+        c.device = cfg->device;
+        c.num_views = cfg->num_views;
+        c.psf_type = cfg->psf_type;
+        c.lambda = cfg->lambda;
+        c.min_value = cfg->min_value;
+        c.max_len = cfg->max_fft_len > 0 ? cfg->max_fft_len : 1152;
+        require(cfg->psf_type >= 0 && cfg->psf_type <= 3, "bad psf_type");
+        Geometry& g = c.geom;
+        for (int d = 0; d < 3; ++d) {
+            g.gdim[d] = cfg->dims[d]; g.goff[d] = 0; g.vol[d] = cfg->dims[d]; g.own_lo[d] = 0; g.own_hi[d] = cfg->dims[d];
+        }
+        int slo = cfg->shard_lo, shi = cfg->shard_hi, z0 = cfg->local_z0, nz = cfg->local_nz;
+        if (shi <= slo) { slo = 0; shi = cfg->dims[2]; }
+        if (nz <= 0) { z0 = 0; nz = cfg->dims[2]; }
+        g.own_lo[2] = slo; g.own_hi[2] = shi; g.goff[2] = z0; g.vol[2] = nz;
+        mvd_context* ctx = new mvd_context();
+        try { ctx->engine = new Engine(c); } catch (...) { delete ctx; throw; }
+        *out = ctx;
+    });
+}
+
+int mvd_destroy(mvd_context* ctx) {
+    return guarded([&] {
+        if (!ctx) return;
+        delete ctx->engine;
+        delete ctx;
+    });
+}
+
+int mvd_set_view(mvd_context* ctx, int v, const float* img, const float* weight) {
+    return guarded([&] { require(ctx && img && weight, "null argument"); ctx->engine->set_view_host(v, img, weight); });
+}
+int mvd_set_view_device(mvd_context* ctx, int v, const float* img, const float* weight) {
+    return guarded([&] { require(ctx && img && weight, "null argument"); ctx->engine->set_view_device(v, img, weight); });
+}
+int mvd_set_psf(mvd_context* ctx, int v, const float* psf, const int kdims[3]) {
+    return guarded([&] {
+        require(ctx && psf && kdims, "null argument");
+        require(kdims[0] > 0 && kdims[1] > 0 && kdims[2] > 0, "empty PSF");
+        ctx->engine->set_psf(v, psf, kdims);
+    });
+}
+int mvd_set_kernels(mvd_context* ctx, int v, const float* k1, const int k1d[3], const float* k2, const int k2d[3]) {
+    return guarded([&] { require(ctx && k1 && k2 && k1d && k2d, "null argument"); ctx->engine->set_kernels(v, k1, k1d, k2, k2d); });
+}
+int mvd_init_views(mvd_context* ctx) {
+    return guarded([&] {
+        require(ctx, "null context");
+        ctx->engine->init_views();
+        // halo this shard needs from its z-neighbours = distance between the owned slab and the first / last tile plane read
+        const Geometry& g = ctx->engine->config().geom;
+        int lo = 0, hi = 0;
+        for (const TileGeom& t : ctx->engine->convolver()->tiles()) {
+            lo = std::max(lo, g.own_lo[2] - t.org[2]);
+            hi = std::max(hi, t.org[2] + ctx->engine->convolver()->tile_dims()[2] - g.own_hi[2]);
+        }
+        ctx->halo_lo = g.own_lo[2] == 0 ? 0 : lo;
+        ctx->halo_hi = g.own_hi[2] == g.gdim[2] ? 0 : hi;
+    });
+}
+int mvd_get_kernel_dims(mvd_context* ctx, int v, int which, int kdims[3]) {
+    return guarded([&] { require(ctx && kdims && (which == 1 || which == 2), "bad argument"); ctx->engine->get_kernel_dims(v, which, kdims); });
+}
+int mvd_get_kernel(mvd_context* ctx, int v, int which, float* out) {
+    return guarded([&] { require(ctx && out && (which == 1 || which == 2), "bad argument"); ctx->engine->get_kernel(v, which, out); });
+}
+int mvd_set_psi(mvd_context* ctx, const float* psi) {
+    return guarded([&] { require(ctx && psi, "null argument"); ctx->engine->set_psi_host(psi); });
+}
+int mvd_get_psi(mvd_context* ctx, float* psi) {
+    return guarded([&] { require(ctx && psi, "null argument"); ctx->engine->get_psi_host(psi); });
+}
+int mvd_set_max_intensities(mvd_context* ctx, const float* mx) {
+    return guarded([&] { require(ctx && mx, "null argument"); ctx->engine->set_max_intensity(mx); });
+}
+int mvd_run_view_update(mvd_context* ctx, int v, double stats[2]) {
+    return guarded([&] {
+        require(ctx, "null context");
+        ctx->engine->view_update(v);
+        IterStats s{0, -1};
+        ctx->engine->fetch_stats(1, &s);
+        if (stats) { stats[0] = s.sum_change; stats[1] = s.max_change; }
+    });
+}
+int mvd_run_iterations(mvd_context* ctx, int n, double* stats) {
+    return guarded([&] {
+        require(ctx && n >= 0, "bad argument");
+        std::vector<IterStats> s((size_t)n * ctx->engine->num_views() + 1);
+        ctx->engine->run_iterations(n, stats ? s.data() : nullptr);
+        if (stats)
+            for (size_t i = 0; i < (size_t)n * ctx->engine->num_views(); ++i) { stats[2 * i] = s[i].sum_change; stats[2 * i + 1] = s[i].max_change; }
+    });
+}
+int mvd_enqueue_view_update(mvd_context* ctx, int v) {
+    return guarded([&] { require(ctx, "null context"); ctx->engine->view_update(v); });
+}
+int mvd_synchronize(mvd_context* ctx) {
+    return guarded([&] { require(ctx, "null context"); ctx->engine->synchronize(); });
+}
+int mvd_fetch_stats(mvd_context* ctx, int count, double* stats) {
+    return guarded([&] {
+        require(ctx && stats && count >= 0, "bad argument");
+        std::vector<IterStats> s((size_t)count + 1, IterStats{0, -1});
+        ctx->engine->fetch_stats(count, s.data());
+        for (int i = 0; i < count; ++i) { stats[2 * i] = s[i].sum_change; stats[2 * i + 1] = s[i].max_change; }
+    });
+}
+int mvd_tile_info(mvd_context* ctx, int tile_dims[3], int* num_tiles, double* ratio, int* launches) {
+    return guarded([&] {
+        require(ctx && ctx->engine->convolver(), "views not initialised");
+        const Convolver* c = ctx->engine->convolver();
+        if (tile_dims) for (int d = 0; d < 3; ++d) tile_dims[d] = c->tile_dims()[d];
+        if (num_tiles) *num_tiles = c->num_tiles();
+        if (ratio) *ratio = c->fft_volume_ratio();
+        if (launches) *launches = ctx->engine->launches_per_view_update();
+    });
+}
+int mvd_halo_planes(mvd_context* ctx, int* lo, int* hi) {
+    return guarded([&] {
+        require(ctx && ctx->engine->convolver(), "views not initialised");
+        if (lo) *lo = ctx->halo_lo;
+        if (hi) *hi = ctx->halo_hi;
+    });
+}
+int mvd_psi_device_ptr(mvd_context* ctx, void** current) {
+    return guarded([&] { require(ctx && current, "null argument"); *current = ctx->engine->psi_device(); });
+}
+int mvd_stream_handle(mvd_context* ctx, void** s) {
+    return guarded([&] { require(ctx && s, "null argument"); *s = (void*)ctx->engine->stream(); });
+}
+
+int mvd_convolve(int device, const float* img, const int dims[3], const float* kernel, const int kdims[3], int ext,
+                 float ext_value, float* out) {
+    return guarded([&] {
+        require(img && dims && kernel && kdims && out, "null argument");
+        require(ext >= 0 && ext <= 2, "bad extension mode");
+        require_device(device);
+        dev::set_device(device);
+        stream_t s = dev::stream_create();
+        try {
+            Tables tables(s);
+            convolve_host(device, s, &tables, 1152, img, dims, kernel, kdims, ext, ext_value, out, false);
+        } catch (...) { dev::stream_destroy(s); throw; }
+        dev::stream_destroy(s);
+    });
+}
+
+int mvd_block_iteration(int device, float* psi_block, const float* img_block, const float* weight_block, const int bd[3],
+                        const float* k1, const int k1d[3], const float* k2, const int k2d[3], float lambda, float min_value,
+                        float max_intensity, double stats[2]) {
+    return guarded([&] {
+        require(psi_block && img_block && weight_block && bd && k1 && k2 && k1d && k2d, "null argument");
+        require_device(device);
+        Engine::Config c;
+        c.device = device;
+        c.num_views = 1;
+        c.psf_type = INDEPENDENT;
+        c.lambda = lambda;
+        c.min_value = min_value;
+        for (int d = 0; d < 3; ++d) { c.geom.gdim[d] = c.geom.vol[d] = bd[d]; c.geom.goff[d] = 0; c.geom.own_lo[d] = 0; c.geom.own_hi[d] = bd[d]; }
+        Engine e(c);
+        e.set_view_host(0, img_block, weight_block);
+        e.set_kernels(0, k1, k1d, k2, k2d);
+        e.init_views();
+        e.set_max_intensity(&max_intensity);
+        e.set_psi_host(psi_block);
+        e.view_update(0);
+        IterStats s{0, -1};
+        e.fetch_stats(1, &s);
+        e.get_psi_host(psi_block);
+        if (stats) { stats[0] = s.sum_change; stats[1] = s.max_change; }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// L1 legacy symbols
+// ---------------------------------------------------------------------------------------------------------------
+static void legacy_convolve(const float* im, const int* imDim, const float* kernel, const int* kernelDim, int devCUDA, float* out) {
+    const int dims[3] = {imDim[2], imDim[1], imDim[0]};         // {z,y,x} -> (x,y,z)  (CUDATools.java:41-49)
+    const int kd[3] = {kernelDim[2], kernelDim[1], kernelDim[0]};
+    require_device(devCUDA);
+    dev::set_device(devCUDA);
+    stream_t s = dev::stream_create();
+    try {
+        Tables tables(s);
+        convolve_host(devCUDA, s, &tables, 1152, im, dims, kernel, kd, EXT_ZERO, 0.f, out, true);
+    } catch (...) { dev::stream_destroy(s); throw; }
+    dev::stream_destroy(s);
+}
+
+void convolution3DfftCUDAInPlace(float* im, int* imDim, float* kernel, int* kernelDim, int devCUDA) {
+    int rc = guarded([&] {
+        require(im && imDim && kernel && kernelDim, "null argument");
+        legacy_convolve(im, imDim, kernel, kernelDim, devCUDA, im);
+    });
+    if (rc) std::fprintf(stderr, "convolution3DfftCUDAInPlace failed: %s\n", g_last_error.c_str());
+}
+
+float* convolution3DfftCUDA(float* im, int* imDim, float* kernel, int* kernelDim, int devCUDA) {
+    float* out = nullptr;
+    int rc = guarded([&] {
+        require(im && imDim && kernel && kernelDim, "null argument");
+        const size_t n = (size_t)imDim[0] * imDim[1] * imDim[2];
+        out = (float*)std::malloc(sizeof(float) * n);
+        require(out != nullptr, "out of host memory");
+        legacy_convolve(im, imDim, kernel, kernelDim, devCUDA, out);
+    });
+    if (rc) {
+        std::fprintf(stderr, "convolution3DfftCUDA failed: %s\n", g_last_error.c_str());
+        std::free(out);
+        return nullptr;
+    }
+    return out;
+}
+
+#ifndef MVD_HOST_EMU
+int getNumDevicesCUDA(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return -1;
+    return n;
+}
+static bool get_props(int dev_, cudaDeviceProp& p) { return cudaGetDeviceProperties(&p, dev_) == cudaSuccess; }
+int getCUDAcomputeCapabilityMajorVersion(int devCUDA) { cudaDeviceProp p; return get_props(devCUDA, p) ? p.major : -1; }
+int getCUDAcomputeCapabilityMinorVersion(int devCUDA) { cudaDeviceProp p; return get_props(devCUDA, p) ? p.minor : -1; }
+void getNameDeviceCUDA(int devCUDA, char* name) {
+    if (!name) return;
+    cudaDeviceProp p;
+    if (!get_props(devCUDA, p)) { name[0] = 0; return; }
+    std::strncpy(name, p.name, 255);
+    name[255] = 0;
+}
+long long getMemDeviceCUDA(int devCUDA) { cudaDeviceProp p; return get_props(devCUDA, p) ? (long long)p.totalGlobalMem : -1; }
+long long getFreeMemDeviceCUDA(int devCUDA) {
+    size_t f = 0, t = 0;
+    if (cudaSetDevice(devCUDA) != cudaSuccess || cudaMemGetInfo(&f, &t) != cudaSuccess) return -1;
+    return (long long)f;
+}
+#else
+int getNumDevicesCUDA(void) { return 1; }
+int getCUDAcomputeCapabilityMajorVersion(int) { return 0; }
+int getCUDAcomputeCapabilityMinorVersion(int) { return 0; }
+void getNameDeviceCUDA(int, char* name) { if (name) std::strcpy(name, "host-emulation (tests only)"); }
+long long getMemDeviceCUDA(int) { return 0; }
+long long getFreeMemDeviceCUDA(int) { return 0; }
+#endif
+
+}  // extern "C"

@@ -1,0 +1,554 @@
+// Engine implementation.  Compiled by nvcc (-x cu) for the product and by g++ with -DMVD_HOST_EMU for the
+// CPU-side unit tests of the index math (tests/host).
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace mvd {
+
+// ------------------------------------------------------------------------------------------------
+// twiddle tables
+// ------------------------------------------------------------------------------------------------
+Tables::~Tables() {
+    for (auto& kv : tw_) dev::free_(kv.second);
+    for (auto& kv : twist_) dev::free_(kv.second);
+}
+const cpx* Tables::tw(int N) {
+    auto it = tw_.find(N);
+    if (it != tw_.end()) return it->second;
+    std::vector<cpx> h(N);
+    for (int k = 0; k < N; ++k) {
+        const double a = 2.0 * M_PI * (double)k / (double)N;
+        h[k] = cpx{(float)std::cos(a), (float)-std::sin(a)};
+    }
+    cpx* d = (cpx*)dev::alloc(sizeof(cpx) * N);
+    dev::h2d(d, h.data(), sizeof(cpx) * N, stream_);
+    dev::sync(stream_);
+    tw_[N] = d;
+    return d;
+}
+const cpx* Tables::twist(int M) {
+    auto it = twist_.find(M);
+    if (it != twist_.end()) return it->second;
+    std::vector<cpx> h(M);
+    for (int m = 0; m < M; ++m) {
+        const double a = M_PI * (double)m / (double)(2 * M);
+        h[m] = cpx{(float)std::cos(a), (float)-std::sin(a)};
+    }
+    cpx* d = (cpx*)dev::alloc(sizeof(cpx) * M);
+    dev::h2d(d, h.data(), sizeof(cpx) * M, stream_);
+    dev::sync(stream_);
+    twist_[M] = d;
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile planner.  Same validity rule as the reference's halo'd blocks (BlockGeneratorFixedSizePrecise.java:68-91,
+// DeconView.java:155-157): a tile's output is trusted where neither of the two chained convolutions read across the
+// tile edge.  Outside the global volume the quotient is known to be 1 (no image data), which is why tiles that
+// contain a volume boundary only need the single-convolution margin there.
+// ------------------------------------------------------------------------------------------------
+AxisTiling plan_axis(int gdim, int a, int b, Reach r1, Reach r2, bool is_x, int max_len) {
+    const int Lsum = r1.lo + r2.lo, Rsum = r1.hi + r2.hi;
+    const int Lmax = std::max(r1.lo, r2.lo), Rmax = std::max(r1.hi, r2.hi);
+    AxisTiling best;
+    for (int len : supported_lengths()) {
+        if (len > max_len) break;
+        const int T = is_x ? 2 * len : len;
+        AxisTiling cur;
+        cur.T = T;
+        int pos = a;
+        int o = (a == 0) ? -Lmax : a - Lsum;
+        bool ok = true;
+        while (pos < b) {
+            int vend = o + T - Rsum;
+            if (b == gdim && o + T >= gdim + Rmax) vend = b;
+            const int hi = std::min(vend, b);
+            if (hi <= pos || cur.tiles.size() > 65536) { ok = false; break; }
+            cur.tiles.push_back(AxisTile{o, pos, hi});
+            pos = hi;
+            o = pos - Lsum;
+        }
+        if (!ok) continue;
+        if (best.T == 0 || cur.cost() < best.cost()) best = cur;
+    }
+    if (best.T == 0) throw Error("no supported FFT length fits this axis (volume + PSF too large for max_len?)");
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small device functors
+// ------------------------------------------------------------------------------------------------
+struct PlaceKernel {   // scatter the (tiny) kernel into a zeroed tile with its centre at the origin
+    const float* k;
+    float* out;
+    int kd0, kd1, kd2, T0, T1, T2;
+    float scale;
+    int negacyclic;
+    MVD_HD void operator()(long long i) const {
+        const int jx = (int)(i % kd0), jy = (int)((i / kd0) % kd1), jz = (int)(i / ((long long)kd0 * kd1));
+        int px = jx - kd0 / 2, py = jy - kd1 / 2, pz = jz - kd2 / 2;
+        float s = scale;
+        if (px < 0) { px += T0; if (negacyclic) s = -s; }     // skew-circular wrap in x
+        if (py < 0) py += T1;
+        if (pz < 0) pz += T2;
+        out[((long long)pz * T1 + py) * T0 + px] = s * k[i];
+    }
+};
+struct ReduceParts1 {
+    const double* ps; const float* pm; int n; double* ts; float* tm;
+    MVD_HD void operator()(long long lane) const {
+        double s = 0.0; float m = -1.f;
+        for (int i = (int)lane; i < n; i += 256) { s += ps[i]; m = pm[i] > m ? pm[i] : m; }
+        ts[lane] = s; tm[lane] = m;
+    }
+};
+struct ReduceParts2 {
+    const double* ts; const float* tm; double* out;
+    MVD_HD void operator()(long long) const {
+        double s = 0.0; float m = -1.f;
+        for (int i = 0; i < 256; ++i) { s += ts[i]; m = tm[i] > m ? tm[i] : m; }
+        out[0] = s; out[1] = (double)m;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Convolver
+// ------------------------------------------------------------------------------------------------
+Convolver::Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], int xmode, int max_len, stream_t s, Tables* tables)
+    : g_(g), xmode_(xmode), stream_(s), tables_(tables) {
+    AxisTiling ax[3];
+    if (xmode == 1) {
+        for (int d = 0; d < 3; ++d) {
+            if (!find_len_ops(g.gdim[d])) throw Error("circular convolution: dimension " + std::to_string(g.gdim[d]) + " is not a supported FFT length");
+            ax[d].T = g.gdim[d];
+            ax[d].tiles.push_back(AxisTile{0, 0, g.gdim[d]});
+        }
+        M_ = ax[0].T;
+    } else {
+        for (int d = 0; d < 3; ++d) ax[d] = plan_axis(g.gdim[d], g.own_lo[d], g.own_hi[d], r1[d], r2[d], d == 0, max_len);
+        M_ = ax[0].T / 2;
+    }
+    for (int d = 0; d < 3; ++d) T_[d] = ax[d].T;
+    ox_ = find_len_ops(M_);
+    oy_ = find_len_ops(T_[1]);
+    oz_ = find_len_ops(T_[2]);
+    if (!ox_ || !oy_ || !oz_) throw Error("internal: planned length without kernels");
+    px_ = (M_ + 3) / 4 * 4;
+    xblocks_ = (T_[1] * T_[2] + ox_->W - 1) / ox_->W;
+    for (const AxisTile& tz : ax[2].tiles)
+        for (const AxisTile& ty : ax[1].tiles)
+            for (const AxisTile& tx : ax[0].tiles) {
+                TileGeom t;
+                t.org[0] = tx.org; t.lo[0] = tx.lo; t.hi[0] = tx.hi;
+                t.org[1] = ty.org; t.lo[1] = ty.lo; t.hi[1] = ty.hi;
+                t.org[2] = tz.org; t.lo[2] = tz.lo; t.hi[2] = tz.hi;
+                tiles_.push_back(t);
+            }
+    work_ = (cpx*)dev::alloc(sizeof(cpx) * tile_elems());
+    dev::zero(work_, sizeof(cpx) * tile_elems(), stream_);   // pitch padding columns stay finite
+}
+Convolver::~Convolver() {
+    dev::free_(work_);
+    dev::free_(kpad_);
+}
+double Convolver::fft_volume_ratio() const {
+    double useful = 0;
+    for (const TileGeom& t : tiles_) useful += (double)(t.hi[0] - t.lo[0]) * (t.hi[1] - t.lo[1]) * (t.hi[2] - t.lo[2]);
+    return (double)tiles_.size() * T_[0] * T_[1] * T_[2] / std::max(useful, 1.0);
+}
+
+XArgs Convolver::base_xargs(const TileGeom& t) const {
+    XArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.cdata = work_;
+    a.px = px_;
+    a.nlines = T_[1] * T_[2];
+    a.ty = T_[1];
+    a.tw = tables_->tw(M_);
+    a.twist = xmode_ == 0 ? tables_->twist(M_) : nullptr;
+    a.xmode = xmode_;
+    for (int d = 0; d < 3; ++d) {
+        a.vol[d] = g_.vol[d]; a.gdim[d] = g_.gdim[d]; a.goff[d] = g_.goff[d];
+        a.org[d] = t.org[d]; a.vlo[d] = t.lo[d]; a.vhi[d] = t.hi[d];
+    }
+    a.ext = EXT_MIRROR;
+    a.ext_value = 0.f;
+    a.min_value = 1e-4f;
+    a.max_intensity = 1.f;
+    return a;
+}
+
+void Convolver::col(int axis, int mode, const cpx* khat) {
+    ColArgs c;
+    c.data = work_;
+    c.khat = khat;
+    c.nx = M_;
+    const LenOps* o = axis == 1 ? oy_ : oz_;
+    c.tw = tables_->tw(o->N);
+    int gy;
+    if (axis == 1) { c.stride_n = px_; c.stride_b = (long long)px_ * T_[1]; gy = T_[2]; }
+    else { c.stride_n = (long long)px_ * T_[1]; c.stride_b = px_; gy = T_[1]; }
+    o->launch_col(mode, c, (M_ + o->W - 1) / o->W, gy, stream_);
+}
+
+cpx* Convolver::build_khat(const float* kernel_host, const int kd[3]) {
+    for (int d = 0; d < 3; ++d)
+        if (kd[d] > T_[d] || kd[d] < 1) throw Error("kernel larger than the FFT tile");
+    const size_t nk = (size_t)kd[0] * kd[1] * kd[2];
+    const size_t nt = (size_t)T_[0] * T_[1] * T_[2];
+    if (!kpad_) kpad_ = (float*)dev::alloc(sizeof(float) * nt);
+    float* kdev = (float*)dev::alloc(sizeof(float) * nk);
+    dev::h2d(kdev, kernel_host, sizeof(float) * nk, stream_);
+    dev::zero(kpad_, sizeof(float) * nt, stream_);
+    const double nfft = (double)M_ * (double)T_[1] * (double)T_[2];
+    PlaceKernel pk{kdev, kpad_, kd[0], kd[1], kd[2], T_[0], T_[1], T_[2], (float)(1.0 / nfft), xmode_ == 0 ? 1 : 0};
+    pfor((long long)nk, pk, stream_);
+    // forward transform of the padded kernel through the very same passes (scrambled order matches by construction)
+    TileGeom t;
+    for (int d = 0; d < 3; ++d) { t.org[d] = 0; t.lo[d] = 0; t.hi[d] = T_[d]; }
+    XArgs a = base_xargs(t);
+    for (int d = 0; d < 3; ++d) { a.vol[d] = T_[d]; a.gdim[d] = T_[d]; a.goff[d] = 0; }
+    a.src = kpad_;
+    a.ext = EXT_ZERO;
+    ox_->launch_x(X_FWD, a, xblocks_, stream_);
+    col(1, COL_FWD, nullptr);
+    col(2, COL_FWD, nullptr);
+    cpx* khat = (cpx*)dev::alloc(sizeof(cpx) * tile_elems());
+    dev::d2d(khat, work_, sizeof(cpx) * tile_elems(), stream_);
+    dev::sync(stream_);
+    dev::free_(kdev);
+    return khat;
+}
+
+void Convolver::conv(const float* src, float* dst, const cpx* khat, int ext, float ext_value) {
+    for (const TileGeom& t : tiles_) {
+        XArgs a = base_xargs(t);
+        a.src = src;
+        a.ext = ext;
+        a.ext_value = ext_value;
+        ox_->launch_x(X_FWD, a, xblocks_, stream_);
+        col(1, COL_FWD, nullptr);
+        col(2, COL_CONV, khat);
+        col(1, COL_INV, nullptr);
+        a.dst = dst;
+        ox_->launch_x(X_INV, a, xblocks_, stream_);
+    }
+}
+
+void Convolver::view_update(const float* psi_in, float* psi_out, const float* img, const float* weight, const cpx* k1hat,
+                            const cpx* k2hat, float lambda, float min_value, float max_intensity, double* part_sum, float* part_max) {
+    int ti = 0;
+    for (const TileGeom& t : tiles_) {
+        XArgs a = base_xargs(t);
+        a.src = psi_in;                                   // P1: mirror-single outside the volume (MultiViewDeconvolutionSeq.java:115)
+        a.ext = EXT_MIRROR;
+        ox_->launch_x(X_FWD, a, xblocks_, stream_);
+        col(1, COL_FWD, nullptr);                         // P2
+        col(2, COL_CONV, k1hat);                          // P3
+        col(1, COL_INV, nullptr);                         // P4
+        a.src = img;                                      // P5: quotient, 1 where there is no image data
+        ox_->launch_x(X_RATIO, a, xblocks_, stream_);
+        col(1, COL_FWD, nullptr);                         // P6
+        col(2, COL_CONV, k2hat);                          // P7
+        col(1, COL_INV, nullptr);                         // P8
+        a.src = psi_in;                                   // P9
+        a.weight = weight;
+        a.dst = psi_out;
+        a.lambda = lambda;
+        a.min_value = min_value;
+        a.max_intensity = max_intensity;
+        a.part_sum = part_sum + (size_t)ti * xblocks_;
+        a.part_max = part_max + (size_t)ti * xblocks_;
+        ox_->launch_x(X_UPDATE, a, xblocks_, stream_);
+        ++ti;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel helpers (host; kernels are a few thousand voxels)
+// ------------------------------------------------------------------------------------------------
+std::vector<float> mirror_kernel(const std::vector<float>& k, const int kd[3]) {
+    // Mirror.mirror (M/process/deconvolution/util/Mirror.java:96-108) applied to every axis: positions p <= dim/2 are swapped
+    // with dim-1-p, so for an even size the two middle samples are swapped twice and stay put ("Quirk C").
+    std::vector<float> cur = k;
+    for (int axis = 0; axis < 3; ++axis) {
+        std::vector<float> out(cur.size());
+        const int n = kd[axis];
+        for (int z = 0; z < kd[2]; ++z)
+            for (int y = 0; y < kd[1]; ++y)
+                for (int x = 0; x < kd[0]; ++x) {
+                    int c[3] = {x, y, z};
+                    int p = c[axis];
+                    int q = n - 1 - p;
+                    if (n % 2 == 0 && (p == n / 2 || p == n / 2 - 1)) q = p;
+                    int s[3] = {x, y, z};
+                    s[axis] = q;
+                    out[((size_t)z * kd[1] + y) * kd[0] + x] = cur[((size_t)s[2] * kd[1] + s[1]) * kd[0] + s[0]];
+                }
+        cur.swap(out);
+    }
+    return cur;
+}
+double sum_kernel(const std::vector<float>& k) {
+    // RealSum-like compensated summation (AdjustInput.sumImg, AdjustInput.java:65-122; exact-sum policy, no double count)
+    double s = 0.0, c = 0.0;
+    for (float v : k) { double y = (double)v - c; double t = s + y; c = (t - s) - y; s = t; }
+    return s;
+}
+void norm_to_sum1(std::vector<float>& k) {   // AdjustInput.normToSum1 (AdjustInput.java:52-58)
+    const double s = sum_kernel(k);
+    for (float& v : k) v = (float)((double)v / s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Engine
+// ------------------------------------------------------------------------------------------------
+Engine::Engine(const Config& c) : cfg_(c) {
+    if (c.num_views < 1) throw Error("need at least one view");
+    for (int d = 0; d < 3; ++d) {
+        const Geometry& g = c.geom;
+        if (g.vol[d] < 1 || g.gdim[d] < 1) throw Error("empty volume");
+        if (g.own_lo[d] < 0 || g.own_hi[d] > g.gdim[d] || g.own_lo[d] >= g.own_hi[d]) throw Error("bad responsibility box");
+        if (g.own_lo[d] < g.goff[d] || g.own_hi[d] > g.goff[d] + g.vol[d]) throw Error("responsibility box outside the local array");
+    }
+    dev::set_device(c.device);
+    stream_ = dev::stream_create();
+    tables_.reset(new Tables(stream_));
+    views_.resize(c.num_views);
+    const size_t bytes = sizeof(float) * local_voxels();
+    psi_[0] = (float*)dev::alloc(bytes);
+    psi_[1] = (float*)dev::alloc(bytes);
+    dev::zero(psi_[0], bytes, stream_);
+    dev::zero(psi_[1], bytes, stream_);
+}
+
+Engine::~Engine() {
+    try { dev::set_device(cfg_.device); dev::sync(stream_); } catch (...) {}
+    for (View& v : views_) {
+        dev::free_(v.img_owned); dev::free_(v.weight_owned); dev::free_(v.k1hat); dev::free_(v.k2hat);
+    }
+    dev::free_(psi_[0]); dev::free_(psi_[1]);
+    dev::free_(part_sum_); dev::free_(part_max_); dev::free_(stats_dev_);
+    conv_.reset();
+    tables_.reset();
+    dev::stream_destroy(stream_);
+}
+
+void Engine::set_view_host(int v, const float* img, const float* weight) {
+    if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
+    dev::set_device(cfg_.device);
+    View& vw = views_[v];
+    const size_t bytes = sizeof(float) * local_voxels();
+    if (!vw.img_owned) vw.img_owned = (float*)dev::alloc(bytes);
+    if (!vw.weight_owned) vw.weight_owned = (float*)dev::alloc(bytes);
+    dev::h2d(vw.img_owned, img, bytes, stream_);
+    dev::h2d(vw.weight_owned, weight, bytes, stream_);
+    vw.img = vw.img_owned;
+    vw.weight = vw.weight_owned;
+}
+void Engine::set_view_device(int v, const float* img, const float* weight) {
+    if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
+    views_[v].img = img;
+    views_[v].weight = weight;
+}
+void Engine::set_psf(int v, const float* psf, const int kd[3]) {
+    if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
+    View& vw = views_[v];
+    const size_t n = (size_t)kd[0] * kd[1] * kd[2];
+    vw.psf.assign(psf, psf + n);
+    for (int d = 0; d < 3; ++d) vw.psf_dims[d] = kd[d];
+    vw.k1.clear(); vw.k2.clear();
+    inited_ = false;
+}
+void Engine::set_kernels(int v, const float* k1, const int k1d[3], const float* k2, const int k2d[3]) {
+    if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
+    View& vw = views_[v];
+    vw.k1.assign(k1, k1 + (size_t)k1d[0] * k1d[1] * k1d[2]);
+    vw.k2.assign(k2, k2 + (size_t)k2d[0] * k2d[1] * k2d[2]);
+    for (int d = 0; d < 3; ++d) { vw.k1d[d] = k1d[d]; vw.k2d[d] = k2d[d]; }
+    vw.psf.clear();
+    inited_ = false;
+}
+
+std::vector<float> Engine::conv_same(const std::vector<float>& in, const int d[3], const std::vector<float>& k, const int kd[3]) {
+    std::vector<float> out(in.size());
+    convolve_host(cfg_.device, stream_, tables_.get(), cfg_.max_len, in.data(), d, k.data(), kd, EXT_ZERO, 0.f, out.data(), false);
+    return out;
+}
+
+// DeconViewPSF.init for every view in list order (DeconViewPSF.java:119-254, DeconViews.java:69-70)
+void Engine::derive_kernels() {
+    const int V = cfg_.num_views;
+    bool any_psf = false;
+    for (View& vw : views_) any_psf = any_psf || !vw.psf.empty();
+    if (!any_psf) return;
+    for (View& vw : views_) {
+        if (vw.psf.empty()) throw Error("either all views get a PSF (set_psf) or all get explicit kernels (set_kernels)");
+        vw.k1 = vw.psf;                       // not yet normalised -- see Quirk B below
+        for (int d = 0; d < 3; ++d) { vw.k1d[d] = vw.psf_dims[d]; vw.k2d[d] = vw.psf_dims[d]; }
+    }
+    for (int v = 0; v < V; ++v) {
+        View& me = views_[v];
+        norm_to_sum1(me.k1);                                                                     // :125
+        if (V == 1 || cfg_.psf_type == INDEPENDENT) {                                            // :127-131
+            me.k2 = mirror_kernel(me.k1, me.k1d);
+        } else if (cfg_.psf_type == EFFICIENT_BAYESIAN) {                                        // :132-195
+            std::vector<float> tmp = mirror_kernel(me.k1, me.k1d);
+            for (int w = 0; w < V; ++w) {
+                if (w == v) continue;
+                // other views' kernel1 is normalised only if their init already ran (w < v): "Quirk B", harmless
+                View& ot = views_[w];
+                std::vector<float> out = conv_same(mirror_kernel(me.k1, me.k1d), me.k1d, ot.k1, ot.k1d);
+                out = conv_same(out, me.k1d, mirror_kernel(ot.k1, ot.k1d), ot.k1d);
+                for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = out[i] * tmp[i];
+            }
+            norm_to_sum1(tmp);
+            me.k2 = tmp;
+        } else if (cfg_.psf_type == OPTIMIZATION_I) {                                            // :196-242
+            std::vector<float> tmp = me.k1;
+            for (int w = 0; w < V; ++w) {
+                if (w == v) continue;
+                View& ot = views_[w];
+                std::vector<float> out = conv_same(me.k1, me.k1d, mirror_kernel(ot.k1, ot.k1d), ot.k1d);
+                for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = out[i] * tmp[i];
+            }
+            norm_to_sum1(tmp);
+            me.k2 = mirror_kernel(tmp, me.k1d);
+        } else {                                                                                 // OPTIMIZATION_II :243-253
+            std::vector<float> e = me.k1;
+            for (size_t i = 0; i < e.size(); ++i) {
+                float r = me.k1[i];
+                for (int p = 1; p < V; ++p) r *= me.k1[i];       // pow by repeated float multiply (:276-284)
+                e[i] = r;
+            }
+            norm_to_sum1(e);
+            me.k2 = mirror_kernel(e, me.k1d);
+        }
+    }
+}
+
+void Engine::init_views() {
+    dev::set_device(cfg_.device);
+    derive_kernels();
+    Reach r1[3] = {{0, 0}, {0, 0}, {0, 0}}, r2[3] = {{0, 0}, {0, 0}, {0, 0}};
+    for (View& vw : views_) {
+        if (vw.k1.empty() || vw.k2.empty()) throw Error("view without kernels: call set_psf or set_kernels for every view");
+        for (int d = 0; d < 3; ++d) {
+            Reach a = reach_of(vw.k1d[d]), b = reach_of(vw.k2d[d]);
+            r1[d].lo = std::max(r1[d].lo, a.lo); r1[d].hi = std::max(r1[d].hi, a.hi);
+            r2[d].lo = std::max(r2[d].lo, b.lo); r2[d].hi = std::max(r2[d].hi, b.hi);
+        }
+    }
+    for (View& vw : views_) { dev::free_(vw.k1hat); dev::free_(vw.k2hat); vw.k1hat = vw.k2hat = nullptr; }
+    conv_.reset(new Convolver(cfg_.geom, r1, r2, 0, cfg_.max_len, stream_, tables_.get()));
+    for (View& vw : views_) {
+        vw.k1hat = conv_->build_khat(vw.k1.data(), vw.k1d);
+        vw.k2hat = conv_->build_khat(vw.k2.data(), vw.k2d);
+    }
+    const size_t nparts = (size_t)conv_->num_tiles() * conv_->parts_per_tile();
+    dev::free_(part_sum_); dev::free_(part_max_);
+    part_sum_ = (double*)dev::alloc(sizeof(double) * (nparts + 256));
+    part_max_ = (float*)dev::alloc(sizeof(float) * (nparts + 256));
+    inited_ = true;
+}
+
+void Engine::get_kernel_dims(int v, int which, int kd[3]) const {
+    const View& vw = views_.at(v);
+    for (int d = 0; d < 3; ++d) kd[d] = which == 1 ? vw.k1d[d] : vw.k2d[d];
+}
+void Engine::get_kernel(int v, int which, float* out) const {
+    const View& vw = views_.at(v);
+    const std::vector<float>& k = which == 1 ? vw.k1 : vw.k2;
+    std::copy(k.begin(), k.end(), out);
+}
+
+void Engine::set_psi_host(const float* psi) {
+    dev::set_device(cfg_.device);
+    dev::h2d(psi_[cur_], psi, sizeof(float) * local_voxels(), stream_);
+    dev::sync(stream_);
+}
+void Engine::get_psi_host(float* psi) {
+    dev::set_device(cfg_.device);
+    dev::d2h(psi, psi_[cur_], sizeof(float) * local_voxels(), stream_);
+    dev::sync(stream_);
+}
+
+int Engine::launches_per_view_update() const { return conv_ ? conv_->launches_per_update() + 2 : 0; }
+
+void Engine::view_update(int v) {
+    if (!inited_) throw Error("init_views() has not been called");
+    if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
+    dev::set_device(cfg_.device);
+    View& vw = views_[v];
+    if (!vw.img || !vw.weight) throw Error("view without image/weight");
+    if (stats_count_ >= stats_cap_) {
+        // grow the statistics ring (keeps earlier entries)
+        const int ncap = stats_cap_ ? stats_cap_ * 2 : 1024;
+        double* n = (double*)dev::alloc(sizeof(double) * 2 * ncap);
+        if (stats_dev_) { dev::d2d(n, stats_dev_, sizeof(double) * 2 * stats_count_, stream_); dev::sync(stream_); dev::free_(stats_dev_); }
+        stats_dev_ = n;
+        stats_cap_ = ncap;
+    }
+    const int nparts = conv_->num_tiles() * conv_->parts_per_tile();
+    conv_->view_update(psi_[cur_], psi_[cur_ ^ 1], vw.img, vw.weight, vw.k1hat, vw.k2hat, cfg_.lambda, cfg_.min_value,
+                       vw.max_intensity, part_sum_, part_max_);
+    // deterministic two-level reduction of the per-CTA partial statistics
+    ReduceParts1 r1{part_sum_, part_max_, nparts, part_sum_ + nparts, part_max_ + nparts};
+    pfor(256, r1, stream_);
+    ReduceParts2 r2{part_sum_ + nparts, part_max_ + nparts, stats_dev_ + 2 * (size_t)stats_count_};
+    pfor(1, r2, stream_);
+    ++stats_count_;
+    cur_ ^= 1;
+}
+
+void Engine::fetch_stats(int count, IterStats* out) {
+    dev::set_device(cfg_.device);
+    if (count > stats_count_) count = stats_count_;
+    std::vector<double> h(2 * (size_t)std::max(count, 1));
+    if (count > 0) dev::d2h(h.data(), stats_dev_ + 2 * (size_t)(stats_count_ - count), sizeof(double) * 2 * count, stream_);
+    dev::sync(stream_);
+    for (int i = 0; i < count; ++i) { out[i].sum_change = h[2 * i]; out[i].max_change = h[2 * i + 1]; }
+}
+
+void Engine::run_iterations(int n, IterStats* out) {
+    stats_count_ = 0;
+    for (int it = 0; it < n; ++it)
+        for (int v = 0; v < cfg_.num_views; ++v) view_update(v);      // OSEM: psi updated after every view
+    if (out) fetch_stats(n * cfg_.num_views, out);
+    else dev::sync(stream_);
+}
+
+void convolve_host(int device, stream_t stream_, Tables* tables, int max_len, const float* src, const int dims[3],
+                   const float* kernel, const int kd[3], int ext, float ext_value, float* dst, bool circular) {
+    dev::set_device(device);
+    Geometry g;
+    Reach r1[3], r2[3];
+    for (int d = 0; d < 3; ++d) {
+        g.gdim[d] = g.vol[d] = dims[d];
+        g.goff[d] = 0; g.own_lo[d] = 0; g.own_hi[d] = dims[d];
+        r1[d] = reach_of(kd[d]);
+        r2[d] = Reach{0, 0};
+    }
+    Convolver cv(g, r1, r2, circular ? 1 : 0, max_len, stream_, tables);
+    const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    float* s = (float*)dev::alloc(sizeof(float) * n);
+    float* d_ = (float*)dev::alloc(sizeof(float) * n);
+    cpx* khat = nullptr;
+    try {
+        dev::h2d(s, src, sizeof(float) * n, stream_);
+        khat = cv.build_khat(kernel, kd);
+        cv.conv(s, d_, khat, ext, ext_value);
+        dev::d2h(dst, d_, sizeof(float) * n, stream_);
+        dev::sync(stream_);
+    } catch (...) {
+        dev::free_(s); dev::free_(d_); dev::free_(khat);
+        throw;
+    }
+    dev::free_(s); dev::free_(d_); dev::free_(khat);
+}
+
+void Convolver::forward_to_ratio(const float*, const float*, const cpx*, const cpx*, int) { throw Error("not implemented"); }
+
+}  // namespace mvd

@@ -1,0 +1,182 @@
+// Host-side engine of the B200 multi-view deconvolution path.
+//
+// Mirrors the reference's object model for this path (net.preibisch.mvrecon.process.deconvolution):
+//   DeconViewPSF  -> kernel1 / kernel2 derivation by PSFTYPE + resident kernel spectra   (DeconViewPSF.java:119-254)
+//   DeconView     -> observed image, weight, PSF of one (virtual) view                     (DeconView.java:118-184)
+//   DeconViews    -> all views, dimension check, PSF init in list order                    (DeconViews.java:44-81)
+//   MultiViewDeconvolutionSeq -> OSEM iteration loop                                       (MultiViewDeconvolutionSeq.java:58-180)
+//   Block / BlockGeneratorFixedSizePrecise -> replaced by the TilePlan below: halo'd FFT tiles sized for HBM/L2
+//                                             instead of host RAM, same validity rule (BlockGeneratorFixedSizePrecise.java:59-131)
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "backend.h"
+
+namespace mvd {
+
+enum PsfType : int { OPTIMIZATION_II = 0, OPTIMIZATION_I = 1, EFFICIENT_BAYESIAN = 2, INDEPENDENT = 3 };
+
+// geometry of the real volumes this engine instance works on (all (x,y,z) order)
+struct Geometry {
+    int gdim[3];     // global fused volume size
+    int goff[3];     // global coordinate of local array element 0
+    int vol[3];      // local array size
+    int own_lo[3];   // responsibility box of this instance (global coords, half open)
+    int own_hi[3];
+};
+
+struct AxisTile { int org, lo, hi; };
+struct AxisTiling { int T = 0; std::vector<AxisTile> tiles; long long cost() const { return (long long)T * (long long)tiles.size(); } };
+
+struct TileGeom { int org[3], lo[3], hi[3]; };
+
+// Reach of a kernel of size k along one axis: output x reads input x - t, t in [-c, k-1-c], c = k/2
+struct Reach { int lo, hi; };
+inline Reach reach_of(int k) { return Reach{k - 1 - k / 2, k / 2}; }
+
+// device twiddle tables, cached per length
+class Tables {
+  public:
+    explicit Tables(stream_t s) : stream_(s) {}
+    ~Tables();
+    const cpx* tw(int N);       // exp(-2 pi i k / N)
+    const cpx* twist(int M);    // exp(-i pi m / (2M))
+  private:
+    stream_t stream_;
+    std::map<int, cpx*> tw_, twist_;
+};
+
+// A tiled FFT convolution plan for one geometry and one (or two chained) kernel extents.
+class Convolver {
+  public:
+    // r1: reach of the first convolution, r2: reach of the second (all zero for a single convolution).
+    // xmode 0: negacyclic real-packed x axis (halo'd tiles); xmode 1: exact circular convolution at the volume size
+    Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], int xmode, int max_len, stream_t s, Tables* tables);
+    ~Convolver();
+
+    size_t tile_elems() const { return (size_t)px_ * T_[1] * T_[2]; }            // complex elements per spectrum
+    int num_tiles() const { return (int)tiles_.size(); }
+    int parts_per_tile() const { return xblocks_; }
+    const int* tile_dims() const { return T_; }                                   // {Tx(real), Ty, Tz}
+    const std::vector<TileGeom>& tiles() const { return tiles_; }
+    double fft_volume_ratio() const;                                              // FFT-box voxels / useful voxels
+    int launches_per_update() const { return 9 * num_tiles(); }
+
+    // kernel (x fastest, dims kd) -> resident spectrum (scale 1/Nfft folded in); caller owns the buffer
+    cpx* build_khat(const float* kernel_host, const int kd[3]);
+    // dst(own box) = src (*) kernel, src extended by ext
+    void conv(const float* src, float* dst, const cpx* khat, int ext, float ext_value);
+    // one fused view update (P1..P9) over all tiles; partial stats -> part_sum/part_max [num_tiles*parts_per_tile]
+    void view_update(const float* psi_in, float* psi_out, const float* img, const float* weight, const cpx* k1hat,
+                     const cpx* k2hat, float lambda, float min_value, float max_intensity, double* part_sum, float* part_max);
+    // stage-wise entry points (multi-GPU scheme B and the Mul variant reuse them)
+    void forward_to_ratio(const float* psi_in, const float* img, const cpx* k1hat, const cpx* k2hat, int tile);
+
+  private:
+    XArgs base_xargs(const TileGeom& t) const;
+    void col(int axis, int mode, const cpx* khat);
+    Geometry g_;
+    int xmode_;
+    int T_[3];     // real tile extents
+    int M_;        // complex x length
+    int px_;       // complex pitch
+    int xblocks_;
+    const LenOps *ox_, *oy_, *oz_;
+    std::vector<TileGeom> tiles_;
+    stream_t stream_;
+    Tables* tables_;
+    cpx* work_ = nullptr;
+    float* kpad_ = nullptr;
+};
+
+AxisTiling plan_axis(int gdim, int own_lo, int own_hi, Reach r1, Reach r2, bool is_x, int max_len);
+
+// dst = src (*) kernel on the device; host in / host out.  circular: exact circular convolution at the volume size (legacy
+// JNA semantics), otherwise U/FFTConvolution semantics (output = size of src, src extended by ext).
+void convolve_host(int device, stream_t s, Tables* tables, int max_len, const float* src, const int dims[3], const float* kernel,
+                   const int kd[3], int ext, float ext_value, float* dst, bool circular);
+
+struct IterStats { double sum_change; double max_change; };
+
+class Engine {
+  public:
+    struct Config {
+        int device = 0;
+        Geometry geom;
+        int num_views = 0;
+        int psf_type = EFFICIENT_BAYESIAN;
+        float lambda = 0.f;
+        float min_value = 1e-4f;
+        int max_len = 1152;
+    };
+    explicit Engine(const Config& c);
+    ~Engine();
+
+    int num_views() const { return cfg_.num_views; }
+    size_t local_voxels() const { return (size_t)cfg_.geom.vol[0] * cfg_.geom.vol[1] * cfg_.geom.vol[2]; }
+    const Config& config() const { return cfg_; }
+
+    void set_view_host(int v, const float* img, const float* weight);
+    void set_view_device(int v, const float* img, const float* weight);
+    void set_psf(int v, const float* psf, const int kd[3]);
+    void set_kernels(int v, const float* k1, const int k1d[3], const float* k2, const int k2d[3]);
+    void init_views();                                     // DeconViews ctor: kernels by PSFTYPE, tile plan, spectra
+    void get_kernel_dims(int v, int which, int kd[3]) const;
+    void get_kernel(int v, int which, float* out) const;
+
+    void set_psi_host(const float* psi);
+    void get_psi_host(float* psi);
+    float* psi_device() { return psi_[cur_]; }
+    float* psi_next_device() { return psi_[cur_ ^ 1]; }
+    void set_max_intensity(const float* mx) { for (int v = 0; v < cfg_.num_views; ++v) views_[v].max_intensity = mx[v]; }
+    float max_intensity(int v) const { return views_[v].max_intensity; }
+
+    void view_update(int v);                               // asynchronous on the engine stream
+    void fetch_stats(int count, IterStats* out);           // last `count` view updates (synchronises)
+    void run_iterations(int n, IterStats* out /* n*V or null */);
+    void synchronize() { dev::sync(stream_); }
+    stream_t stream() const { return stream_; }
+
+    Convolver* convolver() { return conv_.get(); }
+    const Convolver* convolver() const { return conv_.get(); }
+    int launches_per_view_update() const;
+
+  private:
+    struct View {
+        const float* img = nullptr;
+        const float* weight = nullptr;
+        float* img_owned = nullptr;
+        float* weight_owned = nullptr;
+        std::vector<float> psf, k1, k2;
+        int psf_dims[3] = {0, 0, 0}, k1d[3] = {0, 0, 0}, k2d[3] = {0, 0, 0};
+        cpx* k1hat = nullptr;
+        cpx* k2hat = nullptr;
+        float max_intensity = 1.f;
+    };
+    void derive_kernels();
+    std::vector<float> conv_same(const std::vector<float>& in, const int d[3], const std::vector<float>& k, const int kd[3]);
+
+    Config cfg_;
+    stream_t stream_ = nullptr;
+    std::unique_ptr<Tables> tables_;
+    std::unique_ptr<Convolver> conv_;
+    std::vector<View> views_;
+    float* psi_[2] = {nullptr, nullptr};
+    int cur_ = 0;
+    bool inited_ = false;
+    // statistics
+    double* part_sum_ = nullptr;
+    float* part_max_ = nullptr;
+    double* stats_dev_ = nullptr;   // ring of {sum,max} pairs
+    int stats_cap_ = 0, stats_count_ = 0;
+};
+
+// helpers shared with the C ABI
+std::vector<float> mirror_kernel(const std::vector<float>& k, const int kd[3]);        // Mirror.mirror on all axes (Quirk C kept)
+double sum_kernel(const std::vector<float>& k);
+void norm_to_sum1(std::vector<float>& k);
+
+}  // namespace mvd

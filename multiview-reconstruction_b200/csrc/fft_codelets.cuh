@@ -1,0 +1,287 @@
+// In-register FFT codelets for the multi-view deconvolution passes (sm_100a).
+//
+// Everything on this path is a complex FFT of a length N = 2^a 3^b 5^c that is split into 2 or 3
+// "stages"; in each stage one thread runs a radix-R DFT (R <= 36) entirely in registers.  The
+// transforms are *no-reorder*: the forward transform is decimation-in-frequency and leaves the
+// spectrum in a fixed, scrambled (digit-reversed) order; the inverse is the exact conjugate
+// transpose of the forward flow graph and consumes that order.  Because every operation between a
+// forward and its inverse on this path is point-wise in frequency (spectrum multiply with a kernel
+// spectrum that was produced by the very same forward transform), the scrambled order never has to
+// be undone -- this removes one shared-memory pass per FFT.
+//
+// The header is plain C++17 and also compiles with g++ (tests/host emulation of the kernels).
+#pragma once
+#include <type_traits>
+#include <utility>
+
+#if defined(__CUDACC__)
+#define MVD_HD __host__ __device__ __forceinline__
+#else
+#define MVD_HD inline __attribute__((always_inline))
+#endif
+
+namespace mvd {
+
+struct alignas(8) cpx { float x, y; };
+
+MVD_HD cpx operator+(cpx a, cpx b) { return cpx{a.x + b.x, a.y + b.y}; }
+MVD_HD cpx operator-(cpx a, cpx b) { return cpx{a.x - b.x, a.y - b.y}; }
+MVD_HD cpx cmul(cpx a, cpx b) { return cpx{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+MVD_HD cpx cmul_conj(cpx a, cpx b) { return cpx{a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }  // a * conj(b)
+
+// read-only / streaming loads
+#if defined(__CUDA_ARCH__)
+MVD_HD cpx ld_ro(const cpx* p) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); return cpx{v.x, v.y}; }
+MVD_HD float ld_rof(const float* p) { return __ldg(p); }
+MVD_HD cpx ld_stream(const cpx* p) { const float2 v = *reinterpret_cast<const float2*>(p); return cpx{v.x, v.y}; }
+#else
+MVD_HD cpx ld_ro(const cpx* p) { return *p; }
+MVD_HD float ld_rof(const float* p) { return *p; }
+MVD_HD cpx ld_stream(const cpx* p) { return *p; }
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// compile-time trigonometry (double precision, exact at the octant points)
+// ---------------------------------------------------------------------------------------------
+constexpr double kTwoPi = 6.283185307179586476925286766559005768;
+
+constexpr double cx_sin_small(double x) {  // |x| <= pi/4
+    double x2 = x * x, term = x, sum = x;
+    for (int i = 1; i <= 12; ++i) { term *= -x2 / double((2 * i) * (2 * i + 1)); sum += term; }
+    return sum;
+}
+constexpr double cx_cos_small(double x) {
+    double x2 = x * x, term = 1.0, sum = 1.0;
+    for (int i = 1; i <= 12; ++i) { term *= -x2 / double((2 * i - 1) * (2 * i)); sum += term; }
+    return sum;
+}
+struct cx_pair { double c, s; };
+// cos/sin of 2*pi*p/q for 0 <= p/q <= 1
+constexpr cx_pair cx_cossin_turn(long long p, long long q) {
+    p %= q; if (p < 0) p += q;
+    if (2 * p > q) { cx_pair r = cx_cossin_turn(q - p, q); return cx_pair{r.c, -r.s}; }          // > half turn
+    if (4 * p > q) { cx_pair r = cx_cossin_turn(q - 2 * p, 2 * q); return cx_pair{-r.c, r.s}; }   // (1/4, 1/2]
+    if (8 * p > q) { cx_pair r = cx_cossin_turn(q - 4 * p, 4 * q); return cx_pair{r.s, r.c}; }    // (1/8, 1/4]
+    double x = kTwoPi * double(p) / double(q);
+    return cx_pair{cx_cos_small(x), cx_sin_small(x)};
+}
+
+constexpr int cx_gcd(int a, int b) { return b == 0 ? a : cx_gcd(b, a % b); }
+
+// multiply by the compile-time twiddle exp(-+ 2 pi i K / N)  (INV -> conjugate)
+template <int K, int N, bool INV>
+MVD_HD cpx mul_tw(cpx a) {
+    constexpr int k = ((K % N) + N) % N;
+    if constexpr (k == 0) {
+        return a;
+    } else if constexpr (2 * k == N) {
+        return cpx{-a.x, -a.y};
+    } else if constexpr (4 * k == N) {          // forward: * (-i)
+        return INV ? cpx{-a.y, a.x} : cpx{a.y, -a.x};
+    } else if constexpr (4 * k == 3 * N) {      // forward: * (+i)
+        return INV ? cpx{a.y, -a.x} : cpx{-a.y, a.x};
+    } else if constexpr ((8 * k) % N == 0) {    // odd multiples of 1/8 turn
+        constexpr float h = 0.70710678118654752440f;
+        constexpr int o = (8 * k) / N;          // 1,3,5,7
+        // forward twiddle = cos - i sin
+        constexpr float cs = (o == 1 || o == 7) ? 1.f : -1.f;
+        constexpr float sn0 = (o == 1 || o == 3) ? -1.f : 1.f;   // sign of imaginary part (forward)
+        constexpr float sn = INV ? -sn0 : sn0;
+        // (x + i y)(cs + i sn) h = h (cs x - sn y) + i h (sn x + cs y)
+        return cpx{h * (cs * a.x - sn * a.y), h * (sn * a.x + cs * a.y)};
+    } else {
+        constexpr cx_pair t = cx_cossin_turn(k, N);
+        constexpr float c = float(t.c);
+        constexpr float s = float(INV ? t.s : -t.s);
+        return cpx{a.x * c - a.y * s, a.x * s + a.y * c};
+    }
+}
+
+template <int I, int N, class F>
+MVD_HD void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// prime butterflies (natural order in -> natural order out, in place)
+// ---------------------------------------------------------------------------------------------
+template <bool INV> MVD_HD void bfly2(cpx& a, cpx& b) {
+    cpx t = a - b; a = a + b; b = t;
+}
+template <bool INV> MVD_HD void bfly3(cpx& a, cpx& b, cpx& c) {
+    constexpr float s = 0.86602540378443864676f;
+    cpx t = b + c;
+    cpx d = b - c;
+    cpx u{a.x - 0.5f * t.x, a.y - 0.5f * t.y};
+    a = a + t;
+    // forward: X1 = u + s*(d.y, -d.x) ; X2 = u - s*(d.y, -d.x)
+    cpx r = INV ? cpx{-s * d.y, s * d.x} : cpx{s * d.y, -s * d.x};
+    b = u + r; c = u - r;
+}
+template <bool INV> MVD_HD void bfly4(cpx& a, cpx& b, cpx& c, cpx& d) {
+    cpx t0 = a + c, t1 = a - c, t2 = b + d, t3 = b - d;
+    cpx r = INV ? cpx{-t3.y, t3.x} : cpx{t3.y, -t3.x};   // -+ i * t3
+    a = t0 + t2; c = t0 - t2; b = t1 + r; d = t1 - r;
+}
+template <bool INV> MVD_HD void bfly5(cpx& a, cpx& b, cpx& c, cpx& d, cpx& e) {
+    constexpr float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+    constexpr float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+    cpx t1 = b + e, t2 = c + d, t3 = b - e, t4 = c - d;
+    cpx m1{a.x + c1 * t1.x + c2 * t2.x, a.y + c1 * t1.y + c2 * t2.y};
+    cpx m2{a.x + c2 * t1.x + c1 * t2.x, a.y + c2 * t1.y + c1 * t2.y};
+    cpx n1{s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y};
+    cpx n2{s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y};
+    a = cpx{a.x + t1.x + t2.x, a.y + t1.y + t2.y};
+    // forward: X1 = m1 - i n1, X4 = m1 + i n1, X2 = m2 - i n2, X3 = m2 + i n2
+    cpx r1 = INV ? cpx{-n1.y, n1.x} : cpx{n1.y, -n1.x};
+    cpx r2 = INV ? cpx{-n2.y, n2.x} : cpx{n2.y, -n2.x};
+    b = m1 + r1; e = m1 - r1; c = m2 + r2; d = m2 - r2;
+}
+
+constexpr int first_factor(int R) {
+    return R % 4 == 0 ? 4 : R % 2 == 0 ? 2 : R % 3 == 0 ? 3 : R % 5 == 0 ? 5 : R;
+}
+// frequency index held at position p after the no-reorder forward DFT of length R
+constexpr int freq_of_pos(int R, int p) {
+    if (R == 1) return 0;
+    int r = first_factor(R), m = R / r;
+    return (p / m) + r * freq_of_pos(m, p % m);
+}
+constexpr bool radix_supported(int R) {
+    while (R % 2 == 0) R /= 2;
+    while (R % 3 == 0) R /= 3;
+    while (R % 5 == 0) R /= 5;
+    return R == 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// recursive in-register DFT on a[OFF + i*STR], i in [0,R)
+//   forward: DIF  = (I_r (x) F_m) . D . (B_r (x) I_m)      (output scrambled, see freq_of_pos)
+//   inverse: exact conjugate transpose of the forward (unnormalised)
+// ---------------------------------------------------------------------------------------------
+template <int R, int OFF, int STR, bool INV, int E>
+struct Dft {
+    static MVD_HD void run(cpx (&a)[E]) {
+        if constexpr (R > 1) {
+            static_assert(radix_supported(R), "radix must be 2^a 3^b 5^c");
+            constexpr int r = first_factor(R);
+            constexpr int m = R / r;
+            if constexpr (!INV) {
+                static_for<0, m>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    bfly<r, j, m>(a);
+                    static_for<1, r>([&](auto qc) {
+                        constexpr int q = decltype(qc)::value;
+                        a[OFF + (j + q * m) * STR] = mul_tw<j * q, R, false>(a[OFF + (j + q * m) * STR]);
+                    });
+                });
+                static_for<0, r>([&](auto qc) {
+                    constexpr int q = decltype(qc)::value;
+                    Dft<m, OFF + q * m * STR, STR, false, E>::run(a);
+                });
+            } else {
+                static_for<0, r>([&](auto qc) {
+                    constexpr int q = decltype(qc)::value;
+                    Dft<m, OFF + q * m * STR, STR, true, E>::run(a);
+                });
+                static_for<0, m>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    static_for<1, r>([&](auto qc) {
+                        constexpr int q = decltype(qc)::value;
+                        a[OFF + (j + q * m) * STR] = mul_tw<j * q, R, true>(a[OFF + (j + q * m) * STR]);
+                    });
+                    bfly<r, j, m>(a);
+                });
+            }
+        }
+    }
+    template <int r, int j, int m>
+    static MVD_HD void bfly(cpx (&a)[E]) {
+        constexpr int i0 = OFF + j * STR;
+        constexpr int d = m * STR;
+        if constexpr (r == 2) bfly2<INV>(a[i0], a[i0 + d]);
+        else if constexpr (r == 3) bfly3<INV>(a[i0], a[i0 + d], a[i0 + 2 * d]);
+        else if constexpr (r == 4) bfly4<INV>(a[i0], a[i0 + d], a[i0 + 2 * d], a[i0 + 3 * d]);
+        else bfly5<INV>(a[i0], a[i0 + d], a[i0 + 2 * d], a[i0 + 3 * d], a[i0 + 4 * d]);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// FFT plan: N = R1*R2*R3 (R3 == 1 for two-stage plans), T threads cooperate on one line,
+// W lines (columns of the shared-memory tile) are processed per CTA.
+// ---------------------------------------------------------------------------------------------
+template <int N_, int R1_, int R2_, int R3_, int T_, int W_>
+struct Plan {
+    static constexpr int N = N_, R1 = R1_, R2 = R2_, R3 = R3_, T = T_, W = W_;
+    static constexpr int NSTAGES = (R3_ > 1) ? 3 : 2;
+    static constexpr int BLK1 = N_, BLK2 = N_ / R1_, BLK3 = N_ / (R1_ * R2_);
+    static constexpr int THREADS = T_ * W_;
+    static_assert(R1_ * R2_ * R3_ == N_, "plan radices must multiply to N");
+    static_assert(R2_ > 1, "plans have at least two stages");
+    static_assert(radix_supported(R1_) && radix_supported(R2_) && radix_supported(R3_), "unsupported radix");
+};
+
+// One radix-R butterfly of one stage.  The line is accessed through functors:
+//   src(n) -> cpx, dst(n, cpx);  tw[k] = exp(-2 pi i k / N), k in [0,N).
+// BLK = block length handled by this stage (N for the first stage), S = BLK/R the element stride.
+// Position p of the butterfly (element base + p*S) holds frequency freq_of_pos(R,p) of the radix-R DFT.
+template <int N, int BLK, int R, bool INV, class Src, class Dst>
+MVD_HD void stage_bfly(int g, const cpx* __restrict__ tw, Src&& src, Dst&& dst) {
+    constexpr int S = BLK / R;
+    const int b = g / S;
+    const int j = g - b * S;
+    const int base = b * BLK + j;
+    cpx a[R];
+    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; a[p] = src(base + p * S); });
+    if constexpr (!INV) {
+        Dft<R, 0, 1, false, R>::run(a);
+        if constexpr (S > 1) {
+            static_for<1, R>([&](auto pc) {
+                constexpr int p = decltype(pc)::value;
+                constexpr int f = freq_of_pos(R, p);
+                a[p] = cmul(a[p], ld_ro(tw + (N / BLK) * f * j));
+            });
+        }
+    } else {
+        if constexpr (S > 1) {
+            static_for<1, R>([&](auto pc) {
+                constexpr int p = decltype(pc)::value;
+                constexpr int f = freq_of_pos(R, p);
+                a[p] = cmul_conj(a[p], ld_ro(tw + (N / BLK) * f * j));
+            });
+        }
+        Dft<R, 0, 1, true, R>::run(a);
+    }
+    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; dst(base + p * S, a[p]); });
+}
+
+// last forward stage (S == 1) fused with the spectrum multiply and the first inverse stage:
+//   a <- F_R a ;  a[p] *= khat(base + p) ;  a <- F_R^H a
+template <int N, int BLK, int R, class Src, class Dst, class Khat>
+MVD_HD void stage_conv(int g, Src&& src, Dst&& dst, Khat&& khat) {
+    static_assert(BLK == R, "stage_conv is the last forward stage");
+    const int base = g * BLK;
+    cpx a[R];
+    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; a[p] = src(base + p); });
+    Dft<R, 0, 1, false, R>::run(a);
+    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; a[p] = cmul(a[p], khat(base + p)); });
+    Dft<R, 0, 1, true, R>::run(a);
+    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; dst(base + p, a[p]); });
+}
+
+// frequency index (natural DFT order) stored at line position n after the full forward plan.
+template <class P>
+constexpr int plan_freq_of_pos(int n) {
+    // stage 1: n = j1 + p1*S1 ... generic: position digits (p1, p2, p3) with
+    // n = p1*BLK2 + p2*BLK3 + p3 ; frequency = f1 + R1*(f2 + R2*f3)
+    int p1 = n / P::BLK2, rem = n % P::BLK2;
+    int p2 = rem / P::BLK3, p3 = rem % P::BLK3;
+    int f1 = freq_of_pos(P::R1, p1), f2 = freq_of_pos(P::R2, p2);
+    int f3 = (P::R3 > 1) ? freq_of_pos(P::R3, p3) : 0;
+    return f1 + P::R1 * (f2 + P::R2 * f3);
+}
+
+}  // namespace mvd
