@@ -121,6 +121,11 @@ MVD_API int mvd_halo_planes(mvd_context* ctx, int* lo, int* hi);            /* z
 MVD_API int mvd_psi_device_ptr(mvd_context* ctx, void** current);           /* device address of the current psi buffer    */
 MVD_API int mvd_stream_handle(mvd_context* ctx, void** cuda_stream);
 
+/* Per-pass device timing (CUDA events on the context's stream around every pass launch): slots 0..8 = passes P1..P9 of a
+ * view update.  ms[] are accumulated milliseconds, counts[] the number of launches; reset != 0 clears them.   */
+MVD_API int mvd_set_profiling(mvd_context* ctx, int on);
+MVD_API int mvd_get_pass_times(mvd_context* ctx, double ms[9], long long counts[9], int reset);
+
 /* Generic FFT convolution of a host volume with a host kernel on the device (used by the PSF derivation; exported for
  * tests and callers that need U/FFTConvolution.convolve semantics, U/FFTConvolution.java:490-603): out has the size of img,
  * kernel centre floor(k/2), img extended by `ext`.                                                                      */

@@ -91,6 +91,8 @@ SYMBOLS = {
     "mvd_halo_planes": (C.c_int, [C.c_void_p, _I, _I]),
     "mvd_psi_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "mvd_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mvd_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "mvd_get_pass_times": (C.c_int, [C.c_void_p, _D, C.POINTER(C.c_longlong), C.c_int]),
     "mvd_convolve": (C.c_int, [C.c_int, _F, _I, _F, _I, C.c_int, C.c_float, _F]),
     "mvd_block_iteration": (C.c_int, [C.c_int, _F, _F, _F, _I, _F, _I, _F, _I, C.c_float, C.c_float, C.c_float, _D]),
 }
@@ -301,6 +303,16 @@ class DeconViews:
         self.lib.check(self.lib.dll.mvd_tile_info(self._ctx, td, C.byref(n), C.byref(r), C.byref(l)))
         return {"tile_dims_xyz": (td[0], td[1], td[2]), "num_tiles": n.value, "fft_volume_ratio": r.value,
                 "launches_per_view_update": l.value}
+
+    def set_profiling(self, on: bool):
+        self.lib.check(self.lib.dll.mvd_set_profiling(self._ctx, 1 if on else 0))
+
+    def pass_times(self, reset: bool = True):
+        """accumulated CUDA-event milliseconds and launch counts of passes P1..P9"""
+        ms = (C.c_double * 9)()
+        n = (C.c_longlong * 9)()
+        self.lib.check(self.lib.dll.mvd_get_pass_times(self._ctx, ms, n, 1 if reset else 0))
+        return [float(x) for x in ms], [int(x) for x in n]
 
     def halo_planes(self):
         lo, hi = C.c_int(), C.c_int()

@@ -104,9 +104,11 @@ inline void pfor(long long n, F f, stream_t) { for (long long i = 0; i < n; ++i)
 // per-length kernel registry
 // --------------------------------------------------------------------------------------------
 struct LenOps {
-    int N, R1, R2, R3, T, W;
-    int threads;
+    int N, R1, R2, R3, T, W, XT, XL;
+    int threads, xthreads;
     size_t smem_col, smem_x;
+    int ntw_x;                                   // entries of the x-pass stage twiddle tables
+    void (*fill_xtw)(cpx* out);                  // host: fills ntw_x entries
     void (*launch_col)(int mode, const ColArgs& a, int gx, int gy, stream_t s);
     void (*launch_x)(int kind, const XArgs& a, int nblocks, stream_t s);
 };

@@ -105,15 +105,7 @@ int mvd_init_views(mvd_context* ctx) {
     return guarded([&] {
         require(ctx, "null context");
         ctx->engine->init_views();
-        // halo this shard needs from its z-neighbours = distance between the owned slab and the first / last tile plane read
-        const Geometry& g = ctx->engine->config().geom;
-        int lo = 0, hi = 0;
-        for (const TileGeom& t : ctx->engine->convolver()->tiles()) {
-            lo = std::max(lo, g.own_lo[2] - t.org[2]);
-            hi = std::max(hi, t.org[2] + ctx->engine->convolver()->tile_dims()[2] - g.own_hi[2]);
-        }
-        ctx->halo_lo = g.own_lo[2] == 0 ? 0 : lo;
-        ctx->halo_hi = g.own_hi[2] == g.gdim[2] ? 0 : hi;
+        ctx->engine->halo_needed(ctx->halo_lo, ctx->halo_hi);
     });
 }
 int mvd_get_kernel_dims(mvd_context* ctx, int v, int which, int kdims[3]) {
@@ -185,6 +177,16 @@ int mvd_psi_device_ptr(mvd_context* ctx, void** current) {
 }
 int mvd_stream_handle(mvd_context* ctx, void** s) {
     return guarded([&] { require(ctx && s, "null argument"); *s = (void*)ctx->engine->stream(); });
+}
+
+int mvd_set_profiling(mvd_context* ctx, int on) {
+    return guarded([&] { require(ctx && ctx->engine->convolver(), "views not initialised"); ctx->engine->convolver()->set_profiling(on != 0); });
+}
+int mvd_get_pass_times(mvd_context* ctx, double ms[9], long long counts[9], int reset) {
+    return guarded([&] {
+        require(ctx && ms && counts && ctx->engine->convolver(), "bad argument");
+        ctx->engine->convolver()->collect_pass_times(ms, counts, reset != 0);
+    });
 }
 
 int mvd_convolve(int device, const float* img, const int dims[3], const float* kernel, const int kdims[3], int ext,

@@ -13,6 +13,20 @@ namespace mvd {
 Tables::~Tables() {
     for (auto& kv : tw_) dev::free_(kv.second);
     for (auto& kv : twist_) dev::free_(kv.second);
+    for (auto& kv : xtw_) dev::free_(kv.second);
+}
+const cpx* Tables::xtw(int M) {
+    auto it = xtw_.find(M);
+    if (it != xtw_.end()) return it->second;
+    const LenOps* o = find_len_ops(M);
+    if (!o) throw Error("no kernels for this length");
+    std::vector<cpx> h((size_t)o->ntw_x + 1);
+    o->fill_xtw(h.data());
+    cpx* d = (cpx*)dev::alloc(sizeof(cpx) * h.size());
+    dev::h2d(d, h.data(), sizeof(cpx) * h.size(), stream_);
+    dev::sync(stream_);
+    xtw_[M] = d;
+    return d;
 }
 const cpx* Tables::tw(int N) {
     auto it = tw_.find(N);
@@ -118,6 +132,7 @@ struct ReduceParts2 {
 // ------------------------------------------------------------------------------------------------
 Convolver::Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], int xmode, int max_len, stream_t s, Tables* tables)
     : g_(g), xmode_(xmode), stream_(s), tables_(tables) {
+    if (const char* e = std::getenv("MVD_PREFETCH_DIST")) pf_dist_ = std::atoi(e);
     AxisTiling ax[3];
     if (xmode == 1) {
         for (int d = 0; d < 3; ++d) {
@@ -135,8 +150,8 @@ Convolver::Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], in
     oy_ = find_len_ops(T_[1]);
     oz_ = find_len_ops(T_[2]);
     if (!ox_ || !oy_ || !oz_) throw Error("internal: planned length without kernels");
-    px_ = (M_ + 3) / 4 * 4;
-    xblocks_ = (T_[1] * T_[2] + ox_->W - 1) / ox_->W;
+    px_ = (M_ + 15) / 16 * 16;                            // 128-byte rows: every 16-column segment is one cache line
+    xblocks_ = (T_[1] * T_[2] + ox_->XL - 1) / ox_->XL;
     for (const AxisTile& tz : ax[2].tiles)
         for (const AxisTile& ty : ax[1].tiles)
             for (const AxisTile& tx : ax[0].tiles) {
@@ -152,6 +167,9 @@ Convolver::Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], in
 Convolver::~Convolver() {
     dev::free_(work_);
     dev::free_(kpad_);
+#ifndef MVD_HOST_EMU
+    for (void* e : prof_events_) cudaEventDestroy((cudaEvent_t)e);
+#endif
 }
 double Convolver::fft_volume_ratio() const {
     double useful = 0;
@@ -166,7 +184,7 @@ XArgs Convolver::base_xargs(const TileGeom& t) const {
     a.px = px_;
     a.nlines = T_[1] * T_[2];
     a.ty = T_[1];
-    a.tw = tables_->tw(M_);
+    a.tw = tables_->xtw(M_);
     a.twist = xmode_ == 0 ? tables_->twist(M_) : nullptr;
     a.xmode = xmode_;
     for (int d = 0; d < 3; ++d) {
@@ -177,6 +195,8 @@ XArgs Convolver::base_xargs(const TileGeom& t) const {
     a.ext_value = 0.f;
     a.min_value = 1e-4f;
     a.max_intensity = 1.f;
+    a.pf_dist = pf_dist_;
+    a.nblocks = xblocks_;
     return a;
 }
 
@@ -190,7 +210,10 @@ void Convolver::col(int axis, int mode, const cpx* khat) {
     int gy;
     if (axis == 1) { c.stride_n = px_; c.stride_b = (long long)px_ * T_[1]; gy = T_[2]; }
     else { c.stride_n = (long long)px_ * T_[1]; c.stride_b = px_; gy = T_[1]; }
-    o->launch_col(mode, c, (M_ + o->W - 1) / o->W, gy, stream_);
+    c.gx = (M_ + o->W - 1) / o->W;
+    c.gy = gy;
+    c.pf_dist = pf_dist_;
+    o->launch_col(mode, c, c.gx, gy, stream_);
 }
 
 cpx* Convolver::build_khat(const float* kernel_host, const int kd[3]) {
@@ -244,15 +267,15 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
         XArgs a = base_xargs(t);
         a.src = psi_in;                                   // P1: mirror-single outside the volume (MultiViewDeconvolutionSeq.java:115)
         a.ext = EXT_MIRROR;
-        ox_->launch_x(X_FWD, a, xblocks_, stream_);
-        col(1, COL_FWD, nullptr);                         // P2
-        col(2, COL_CONV, k1hat);                          // P3
-        col(1, COL_INV, nullptr);                         // P4
+        mark(0); ox_->launch_x(X_FWD, a, xblocks_, stream_);
+        mark(1); col(1, COL_FWD, nullptr);                // P2
+        mark(2); col(2, COL_CONV, k1hat);                 // P3
+        mark(3); col(1, COL_INV, nullptr);                // P4
         a.src = img;                                      // P5: quotient, 1 where there is no image data
-        ox_->launch_x(X_RATIO, a, xblocks_, stream_);
-        col(1, COL_FWD, nullptr);                         // P6
-        col(2, COL_CONV, k2hat);                          // P7
-        col(1, COL_INV, nullptr);                         // P8
+        mark(4); ox_->launch_x(X_RATIO, a, xblocks_, stream_);
+        mark(5); col(1, COL_FWD, nullptr);                // P6
+        mark(6); col(2, COL_CONV, k2hat);                 // P7
+        mark(7); col(1, COL_INV, nullptr);                // P8
         a.src = psi_in;                                   // P9
         a.weight = weight;
         a.dst = psi_out;
@@ -261,7 +284,8 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
         a.max_intensity = max_intensity;
         a.part_sum = part_sum + (size_t)ti * xblocks_;
         a.part_max = part_max + (size_t)ti * xblocks_;
-        ox_->launch_x(X_UPDATE, a, xblocks_, stream_);
+        mark(8); ox_->launch_x(X_UPDATE, a, xblocks_, stream_);
+        mark(-1);
         ++ti;
     }
 }
@@ -441,6 +465,10 @@ void Engine::init_views() {
             r2[d].lo = std::max(r2[d].lo, b.lo); r2[d].hi = std::max(r2[d].hi, b.hi);
         }
     }
+    halo_lo_ = cfg_.geom.own_lo[2] == 0 ? 0 : r1[2].lo + r2[2].lo;
+    halo_hi_ = cfg_.geom.own_hi[2] == cfg_.geom.gdim[2] ? 0 : r1[2].hi + r2[2].hi;
+    if (cfg_.geom.own_lo[2] - halo_lo_ < cfg_.geom.goff[2] || cfg_.geom.own_hi[2] + halo_hi_ > cfg_.geom.goff[2] + cfg_.geom.vol[2])
+        throw Error("sharded context: the local arrays do not contain the halo planes (k1z/2 + k2z/2 per interior side)");
     for (View& vw : views_) { dev::free_(vw.k1hat); dev::free_(vw.k2hat); vw.k1hat = vw.k2hat = nullptr; }
     conv_.reset(new Convolver(cfg_.geom, r1, r2, 0, cfg_.max_len, stream_, tables_.get()));
     for (View& vw : views_) {
@@ -549,6 +577,41 @@ void convolve_host(int device, stream_t stream_, Tables* tables, int max_len, co
     dev::free_(s); dev::free_(d_); dev::free_(khat);
 }
 
-void Convolver::forward_to_ratio(const float*, const float*, const cpx*, const cpx*, int) { throw Error("not implemented"); }
+// ------------------------------------------------------------------------------------------------
+// per-pass event timing: an event is recorded in front of every pass launch (and one behind the last); the time between
+// consecutive events is attributed to the pass launched in between.
+// ------------------------------------------------------------------------------------------------
+void Convolver::mark(int pass) {
+#ifndef MVD_HOST_EMU
+    if (!prof_on_) return;
+    if (prof_used_ == prof_events_.size()) {
+        cudaEvent_t e;
+        MVD_CUDA_CHECK(cudaEventCreate(&e));
+        prof_events_.push_back((void*)e);
+        prof_ids_.push_back(-1);
+    }
+    MVD_CUDA_CHECK(cudaEventRecord((cudaEvent_t)prof_events_[prof_used_], stream_));
+    prof_ids_[prof_used_] = pass;
+    ++prof_used_;
+#else
+    (void)pass;
+#endif
+}
+void Convolver::collect_pass_times(double ms[9], long long counts[9], bool reset) {
+#ifndef MVD_HOST_EMU
+    dev::sync(stream_);
+    for (size_t i = 0; i + 1 < prof_used_; ++i) {
+        const int id = prof_ids_[i];
+        if (id < 0 || id > 8) continue;
+        float t = 0.f;
+        MVD_CUDA_CHECK(cudaEventElapsedTime(&t, (cudaEvent_t)prof_events_[i], (cudaEvent_t)prof_events_[i + 1]));
+        prof_ms_[id] += t;
+        prof_n_[id] += 1;
+    }
+    prof_used_ = 0;
+#endif
+    for (int i = 0; i < 9; ++i) { ms[i] = prof_ms_[i]; counts[i] = prof_n_[i]; }
+    if (reset) for (int i = 0; i < 9; ++i) { prof_ms_[i] = 0; prof_n_[i] = 0; }
+}
 
 }  // namespace mvd

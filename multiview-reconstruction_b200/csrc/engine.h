@@ -44,9 +44,10 @@ class Tables {
     ~Tables();
     const cpx* tw(int N);       // exp(-2 pi i k / N)
     const cpx* twist(int M);    // exp(-i pi m / (2M))
+    const cpx* xtw(int M);      // per-position stage twiddles of the x passes (LenOps::fill_xtw)
   private:
     stream_t stream_;
-    std::map<int, cpx*> tw_, twist_;
+    std::map<int, cpx*> tw_, twist_, xtw_;
 };
 
 // A tiled FFT convolution plan for one geometry and one (or two chained) kernel extents.
@@ -72,8 +73,9 @@ class Convolver {
     // one fused view update (P1..P9) over all tiles; partial stats -> part_sum/part_max [num_tiles*parts_per_tile]
     void view_update(const float* psi_in, float* psi_out, const float* img, const float* weight, const cpx* k1hat,
                      const cpx* k2hat, float lambda, float min_value, float max_intensity, double* part_sum, float* part_max);
-    // stage-wise entry points (multi-GPU scheme B and the Mul variant reuse them)
-    void forward_to_ratio(const float* psi_in, const float* img, const cpx* k1hat, const cpx* k2hat, int tile);
+    // per-pass CUDA-event timing (bench.py's roofline leg): P1..P9 -> slots 0..8
+    void set_profiling(bool on) { prof_on_ = on; }
+    void collect_pass_times(double ms[9], long long counts[9], bool reset);
 
   private:
     XArgs base_xargs(const TileGeom& t) const;
@@ -90,6 +92,15 @@ class Convolver {
     Tables* tables_;
     cpx* work_ = nullptr;
     float* kpad_ = nullptr;
+    int pf_dist_ = 148;    // software L2 prefetch distance in CTAs (one CTA per SM ahead; MVD_PREFETCH_DIST overrides)
+    // profiling
+    void mark(int pass);
+    bool prof_on_ = false;
+    std::vector<void*> prof_events_;
+    std::vector<int> prof_ids_;
+    size_t prof_used_ = 0;
+    double prof_ms_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_n_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 AxisTiling plan_axis(int gdim, int own_lo, int own_hi, Reach r1, Reach r2, bool is_x, int max_len);
@@ -143,6 +154,8 @@ class Engine {
     Convolver* convolver() { return conv_.get(); }
     const Convolver* convolver() const { return conv_.get(); }
     int launches_per_view_update() const;
+    // z planes beyond the owned slab whose psi / image values the two chained convolutions actually read
+    void halo_needed(int& lo, int& hi) const { lo = halo_lo_; hi = halo_hi_; }
 
   private:
     struct View {
@@ -167,6 +180,7 @@ class Engine {
     float* psi_[2] = {nullptr, nullptr};
     int cur_ = 0;
     bool inited_ = false;
+    int halo_lo_ = 0, halo_hi_ = 0;
     // statistics
     double* part_sum_ = nullptr;
     float* part_max_ = nullptr;

@@ -29,6 +29,13 @@ MVD_HD cpx operator-(cpx a, cpx b) { return cpx{a.x - b.x, a.y - b.y}; }
 MVD_HD cpx cmul(cpx a, cpx b) { return cpx{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 MVD_HD cpx cmul_conj(cpx a, cpx b) { return cpx{a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }  // a * conj(b)
 
+// L2 prefetch of the 128-byte line containing p (no-op on the host)
+#if defined(__CUDA_ARCH__)
+MVD_HD void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+MVD_HD void prefetch_l2(const void*) {}
+#endif
+
 // read-only / streaming loads
 #if defined(__CUDA_ARCH__)
 MVD_HD cpx ld_ro(const cpx* p) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); return cpx{v.x, v.y}; }
@@ -209,50 +216,80 @@ struct Dft {
     }
 };
 
+// R consecutive complex values <-> global memory; 16-byte vector accesses when R is even (callers guarantee 16-byte
+// alignment in that case: line pitch is a multiple of 4 elements and the element offset a multiple of R)
+template <int R>
+MVD_HD void st_vec(cpx* o, const cpx (&a)[R]) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (R % 2 == 0) {
+        static_for<0, R / 2>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            reinterpret_cast<float4*>(o)[i] = make_float4(a[2 * i].x, a[2 * i].y, a[2 * i + 1].x, a[2 * i + 1].y);
+        });
+        return;
+    }
+#endif
+    static_for<0, R>([&](auto ic) { constexpr int i = decltype(ic)::value; o[i] = a[i]; });
+}
+template <int R>
+MVD_HD void ld_vec(const cpx* o, cpx (&a)[R]) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (R % 2 == 0) {
+        static_for<0, R / 2>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            const float4 v = reinterpret_cast<const float4*>(o)[i];
+            a[2 * i] = cpx{v.x, v.y}; a[2 * i + 1] = cpx{v.z, v.w};
+        });
+        return;
+    }
+#endif
+    static_for<0, R>([&](auto ic) { constexpr int i = decltype(ic)::value; a[i] = o[i]; });
+}
+
 // ---------------------------------------------------------------------------------------------
-// FFT plan: N = R1*R2*R3 (R3 == 1 for two-stage plans), T threads cooperate on one line,
-// W lines (columns of the shared-memory tile) are processed per CTA.
+// FFT plan: N = R1*R2*R3 (R3 == 1 for two-stage plans).
+//   column passes (y/z axis): T threads cooperate on one column, W columns (128-byte row segments) per CTA
+//   x passes (contiguous lines): XT threads cooperate on one line, XL lines per CTA
 // ---------------------------------------------------------------------------------------------
-template <int N_, int R1_, int R2_, int R3_, int T_, int W_>
+template <int N_, int R1_, int R2_, int R3_, int T_, int W_, int XT_ = N_ / R1_, int XL_ = 8>
 struct Plan {
-    static constexpr int N = N_, R1 = R1_, R2 = R2_, R3 = R3_, T = T_, W = W_;
+    static constexpr int N = N_, R1 = R1_, R2 = R2_, R3 = R3_, T = T_, W = W_, XT = XT_, XL = XL_;
     static constexpr int NSTAGES = (R3_ > 1) ? 3 : 2;
     static constexpr int BLK1 = N_, BLK2 = N_ / R1_, BLK3 = N_ / (R1_ * R2_);
     static constexpr int THREADS = T_ * W_;
+    static constexpr int XTHREADS = XT_ * XL_;
     static_assert(R1_ * R2_ * R3_ == N_, "plan radices must multiply to N");
     static_assert(R2_ > 1, "plans have at least two stages");
     static_assert(radix_supported(R1_) && radix_supported(R2_) && radix_supported(R3_), "unsupported radix");
 };
 
+// multiply a[1..R) by per-position twiddles twp(p) (conjugated for the inverse)
+template <int R, bool INV, class TwP>
+MVD_HD void apply_tw(cpx (&a)[R], TwP&& twp) {
+    static_for<1, R>([&](auto pc) {
+        constexpr int p = decltype(pc)::value;
+        a[p] = INV ? cmul_conj(a[p], twp(pc)) : cmul(a[p], twp(pc));   // twp receives an integral_constant
+    });
+}
+
 // One radix-R butterfly of one stage.  The line is accessed through functors:
-//   src(n) -> cpx, dst(n, cpx);  tw[k] = exp(-2 pi i k / N), k in [0,N).
+//   src(n) -> cpx, dst(n, cpx);  twf(k) -> exp(-2 pi i k / N), k in [0,N)   (global or shared-memory table).
 // BLK = block length handled by this stage (N for the first stage), S = BLK/R the element stride.
 // Position p of the butterfly (element base + p*S) holds frequency freq_of_pos(R,p) of the radix-R DFT.
-template <int N, int BLK, int R, bool INV, class Src, class Dst>
-MVD_HD void stage_bfly(int g, const cpx* __restrict__ tw, Src&& src, Dst&& dst) {
+template <int N, int BLK, int R, bool INV, class TwF, class Src, class Dst>
+MVD_HD void stage_bfly(int g, TwF&& twf, Src&& src, Dst&& dst) {
     constexpr int S = BLK / R;
     const int b = g / S;
     const int j = g - b * S;
     const int base = b * BLK + j;
     cpx a[R];
     static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; a[p] = src(base + p * S); });
+    auto twp = [&](auto pc) { constexpr int f = freq_of_pos(R, decltype(pc)::value); return twf((N / BLK) * f * j); };
     if constexpr (!INV) {
         Dft<R, 0, 1, false, R>::run(a);
-        if constexpr (S > 1) {
-            static_for<1, R>([&](auto pc) {
-                constexpr int p = decltype(pc)::value;
-                constexpr int f = freq_of_pos(R, p);
-                a[p] = cmul(a[p], ld_ro(tw + (N / BLK) * f * j));
-            });
-        }
+        if constexpr (S > 1) apply_tw<R, false>(a, twp);
     } else {
-        if constexpr (S > 1) {
-            static_for<1, R>([&](auto pc) {
-                constexpr int p = decltype(pc)::value;
-                constexpr int f = freq_of_pos(R, p);
-                a[p] = cmul_conj(a[p], ld_ro(tw + (N / BLK) * f * j));
-            });
-        }
+        if constexpr (S > 1) apply_tw<R, true>(a, twp);
         Dft<R, 0, 1, true, R>::run(a);
     }
     static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; dst(base + p * S, a[p]); });

@@ -5,48 +5,52 @@
 
 namespace mvd {
 
-template <class P>
-constexpr int plan_min_blocks() {
-    // aim for 3 resident CTAs per SM when shared memory and the 2048-thread limit allow it
-    constexpr size_t smem = sizeof(cpx) * P::N * (P::W + 1) + 1024;
-    int by_smem = int((227u * 1024u) / smem);
-    int by_thr = 2048 / P::THREADS;
+constexpr int min_blocks_for(size_t smem_bytes, int threads, int want) {
+    // resident CTAs per SM we ask the compiler to make room for: bounded by shared memory, the 2048-thread limit and a
+    // floor of 64 registers per thread
+    int by_smem = int((227u * 1024u) / (smem_bytes + 1024));
+    int by_thr = 2048 / threads;
     int b = by_smem < by_thr ? by_smem : by_thr;
-    if (b > 3) b = 3;
-    // do not ask for fewer than 64 registers per thread
-    while (b > 1 && 65536 / (P::THREADS * b) < 64) --b;
+    if (b > want) b = want;
+    while (b > 1 && 65536 / (threads * b) < 64) --b;
     return b < 1 ? 1 : b;
 }
+template <class P> constexpr int col_min_blocks() { return min_blocks_for(ColSmem<P>::bytes(), P::THREADS, 3); }
+template <class P> constexpr int x_min_blocks() { return min_blocks_for(XLay<P>::bytes(), P::XTHREADS, 4); }
 
 #ifndef MVD_HOST_EMU
 template <class P, int MODE>
-__global__ void __launch_bounds__(P::THREADS, plan_min_blocks<P>()) col_kernel(const ColArgs a) {
+__global__ void __launch_bounds__(P::THREADS, col_min_blocks<P>()) col_kernel(const ColArgs a) {
     extern __shared__ __align__(16) unsigned char mvd_smem[];
     DevExec ex;
     col_pass_body<P, MODE>(ex, a, (int)blockIdx.x, (int)blockIdx.y, reinterpret_cast<cpx*>(mvd_smem));
 }
 template <class P, int KIND>
-__global__ void __launch_bounds__(P::THREADS, plan_min_blocks<P>()) x_kernel(const XArgs a) {
+__global__ void __launch_bounds__(P::XTHREADS, x_min_blocks<P>()) x_kernel(const XArgs a) {
     extern __shared__ __align__(16) unsigned char mvd_smem[];
     DevExec ex;
     cpx* sm = reinterpret_cast<cpx*>(mvd_smem);
-    LineInfo* li = reinterpret_cast<LineInfo*>(sm + XSmem<P>::TILE);
+    LineInfo* li = reinterpret_cast<LineInfo*>(sm + XLay<P>::TILE + XLay<P>::NTW);
     x_pass_body<P, KIND>(ex, a, (int)blockIdx.x, sm, li);
 }
 #endif
 
+inline int carveout_pref() {   // MVD_CARVEOUT: -1 = driver default, 0..100 = preferred shared-memory carveout in percent
+    static const int v = [] { const char* e = std::getenv("MVD_CARVEOUT"); return e ? std::atoi(e) : -1; }();
+    return v;
+}
+
 template <class P>
 struct LenImpl {
-    static constexpr size_t smem_col = sizeof(cpx) * P::N * P::W;
-    static constexpr size_t smem_x = XSmem<P>::bytes() > sizeof(double) * P::THREADS + sizeof(float) * P::THREADS
-                                         ? XSmem<P>::bytes()
-                                         : sizeof(double) * P::THREADS + sizeof(float) * P::THREADS + sizeof(LineInfo) * P::W;
+    static constexpr size_t smem_col = ColSmem<P>::bytes();
+    static constexpr size_t smem_x = XLay<P>::bytes();
+    static_assert(sizeof(cpx) * XLay<P>::TILE >= (sizeof(double) + sizeof(float)) * P::XTHREADS, "reduction scratch must fit in the tile");
 
     template <int MODE>
     static void col(const ColArgs& a, int gx, int gy, stream_t s) {
 #ifdef MVD_HOST_EMU
         (void)s;
-        std::vector<cpx> sm(P::N * P::W);
+        std::vector<cpx> sm(smem_col / sizeof(cpx) + 1);
         HostExec ex(P::THREADS);
         for (int by = 0; by < gy; ++by)
             for (int bx = 0; bx < gx; ++bx) col_pass_body<P, MODE>(ex, a, bx, by, sm.data());
@@ -54,6 +58,7 @@ struct LenImpl {
         static bool attr_done = false;
         if (!attr_done) {
             MVD_CUDA_CHECK(cudaFuncSetAttribute(col_kernel<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
+            if (carveout_pref() >= 0) MVD_CUDA_CHECK(cudaFuncSetAttribute(col_kernel<P, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pref()));
             attr_done = true;
         }
         col_kernel<P, MODE><<<dim3(gx, gy), P::THREADS, smem_col, s>>>(a);
@@ -66,16 +71,17 @@ struct LenImpl {
         (void)s;
         std::vector<unsigned char> raw(smem_x + 16);
         cpx* sm = reinterpret_cast<cpx*>(raw.data());
-        LineInfo* li = reinterpret_cast<LineInfo*>(sm + XSmem<P>::TILE);
-        HostExec ex(P::THREADS);
+        LineInfo* li = reinterpret_cast<LineInfo*>(sm + XLay<P>::TILE + XLay<P>::NTW);
+        HostExec ex(P::XTHREADS);
         for (int bx = 0; bx < nblocks; ++bx) x_pass_body<P, KIND>(ex, a, bx, sm, li);
 #else
         static bool attr_done = false;
         if (!attr_done) {
             MVD_CUDA_CHECK(cudaFuncSetAttribute(x_kernel<P, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+            if (carveout_pref() >= 0) MVD_CUDA_CHECK(cudaFuncSetAttribute(x_kernel<P, KIND>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pref()));
             attr_done = true;
         }
-        x_kernel<P, KIND><<<nblocks, P::THREADS, smem_x, s>>>(a);
+        x_kernel<P, KIND><<<nblocks, P::XTHREADS, smem_x, s>>>(a);
         MVD_CUDA_CHECK(cudaGetLastError());
 #endif
     }
@@ -97,12 +103,13 @@ struct LenImpl {
         }
     }
     static const LenOps* ops() {
-        static const LenOps o = {P::N, P::R1, P::R2, P::R3, P::T, P::W, P::THREADS, smem_col, smem_x, &launch_col, &launch_x};
+        static const LenOps o = {P::N, P::R1, P::R2, P::R3, P::T, P::W, P::XT, P::XL, P::THREADS, P::XTHREADS, smem_col, smem_x,
+                                 XLay<P>::NTW, &fill_xtw<P>, &launch_col, &launch_x};
         return &o;
     }
 };
 
 }  // namespace mvd
 
-#define MVD_DEFINE_LEN(N, R1, R2, R3, T, W) \
-    namespace mvd { const LenOps* len_ops_##N() { return LenImpl<Plan<N, R1, R2, R3, T, W>>::ops(); } }
+#define MVD_DEFINE_LEN(N, R1, R2, R3, T, W, XT, XL) \
+    namespace mvd { const LenOps* len_ops_##N() { return LenImpl<Plan<N, R1, R2, R3, T, W, XT, XL>>::ops(); } }

@@ -37,8 +37,8 @@ static int test_plan() {
     std::vector<cpx> khat(data.size());
     for (auto& c : khat) c = cpx{U(rng), U(rng)};
 
-    ColArgs a{data.data(), khat.data(), tw.data(), stride_n, stride_b, nx};
-    std::vector<cpx> sm(N * W);
+    ColArgs a{data.data(), khat.data(), tw.data(), stride_n, stride_b, nx, 0, 0, 0};
+    std::vector<cpx> sm(N * W + N);
     HostExec ex(P::THREADS);
     const int gx = (nx + W - 1) / W;
     auto run = [&](auto modec) {
