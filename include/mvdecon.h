@@ -77,6 +77,11 @@ typedef struct mvd_config {
     int shard_lo, shard_hi;
     int local_z0, local_nz;
     int max_fft_len;     /* 0 = default (1152); caps the FFT tile edge                                                  */
+    /* AdjustInput.sumImg adds sums[0] and then loops over ALL portion sums including index 0 (AdjustInput.java:115-119), i.e. the
+     * first portion (first floor(size/numPortions) samples, numPortions = max(T, size/64^3), T = max(4, #threads),
+     * FusionTools.java:1287-1329, Threads.java:40) is counted twice, so the reference's "normalised" kernels do not sum to 1 and
+     * the result depends on the thread count.  0 = exact sum (default); T > 0 reproduces the reference run with T ImageJ threads. */
+    int norm_quirk_threads;
 } mvd_config;
 
 MVD_API const char* mvd_last_error(void);                     /* thread-local message of the last failing call          */

@@ -51,7 +51,7 @@ class MvdError(RuntimeError):
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int), ("dims", C.c_int * 3), ("num_views", C.c_int), ("psf_type", C.c_int),
                 ("lambda_", C.c_float), ("min_value", C.c_float), ("shard_lo", C.c_int), ("shard_hi", C.c_int),
-                ("local_z0", C.c_int), ("local_nz", C.c_int), ("max_fft_len", C.c_int)]
+                ("local_z0", C.c_int), ("local_nz", C.c_int), ("max_fft_len", C.c_int), ("norm_quirk_threads", C.c_int)]
 
 
 _F = C.POINTER(C.c_float)
@@ -184,6 +184,30 @@ def lib() -> Lib:
 # =====================================================================================================================
 # Host-side mirror of the reference's operator interface for this path
 # =====================================================================================================================
+class DeviceArray:
+    """A caller-owned float32 volume that already lives in device memory (zero-copy hand-over to the context).
+    `owner` keeps the backing object (e.g. a torch tensor) alive."""
+
+    def __init__(self, ptr: int, shape_zyx: Sequence[int], owner=None):
+        self.ptr = int(ptr)
+        self.shape = tuple(int(x) for x in shape_zyx)
+        self.ndim = len(self.shape)
+        self.owner = owner
+
+    @staticmethod
+    def from_torch(t) -> "DeviceArray":
+        assert t.is_cuda and t.is_contiguous() and str(t.dtype) == "torch.float32"
+        return DeviceArray(t.data_ptr(), tuple(t.shape), t)
+
+
+class RawDeviceBuffer:
+    """__cuda_array_interface__ view of raw device memory (lets torch / cupy wrap the context's psi buffer)."""
+
+    def __init__(self, ptr: int, shape: Sequence[int], typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
 class IterationStatistics:
     """ComputeBlockThread.IterationStatistics (M/process/deconvolution/iteration/ComputeBlockThread.java:64-68)."""
 
@@ -220,8 +244,8 @@ class DeconView:
 
     def __init__(self, image: np.ndarray, weight: np.ndarray, kernel: np.ndarray, psfType: PSFTYPE = PSFTYPE.INDEPENDENT,
                  title: Optional[str] = None):
-        self.image = _f32(image)
-        self.weight = _f32(weight)
+        self.image = image if isinstance(image, DeviceArray) else _f32(image)
+        self.weight = weight if isinstance(weight, DeviceArray) else _f32(weight)
         if self.image.shape != self.weight.shape or self.image.ndim != 3:
             raise MvdError("image and weight must be 3-d volumes of identical size")
         self.psf = DeconViewPSF(kernel, psfType)
@@ -243,7 +267,7 @@ class DeconViews:
 
     def __init__(self, views: Sequence[DeconView], device: int = 0, lambda_: float = 0.0, min_value: float = minValue,
                  shard: Optional[Tuple[int, int, int, int]] = None, global_dims_zyx: Optional[Sequence[int]] = None,
-                 max_fft_len: int = 0, library: Optional[Lib] = None):
+                 max_fft_len: int = 0, norm_quirk_threads: int = 0, library: Optional[Lib] = None):
         self.lib = library or lib()
         self.views = list(views)
         if not self.views:
@@ -268,11 +292,17 @@ class DeconViews:
         if shard is not None:
             cfg.shard_lo, cfg.shard_hi, cfg.local_z0, cfg.local_nz = (int(x) for x in shard)
         cfg.max_fft_len = int(max_fft_len)
+        cfg.norm_quirk_threads = int(norm_quirk_threads)      # 0 = exact sums; T reproduces AdjustInput.sumImg for T threads
         self._ctx = C.c_void_p()
         self.lib.check(self.lib.dll.mvd_create(C.byref(cfg), C.byref(self._ctx)))
         try:
             for i, v in enumerate(self.views):
-                self.lib.check(self.lib.dll.mvd_set_view(self._ctx, i, _fp(v.image), _fp(v.weight)))
+                if isinstance(v.image, DeviceArray) or isinstance(v.weight, DeviceArray):
+                    if not (isinstance(v.image, DeviceArray) and isinstance(v.weight, DeviceArray)):
+                        raise MvdError("image and weight of a view must both be host arrays or both DeviceArrays")
+                    self.lib.check(self.lib.dll.mvd_set_view_device(self._ctx, i, C.c_void_p(v.image.ptr), C.c_void_p(v.weight.ptr)))
+                else:
+                    self.lib.check(self.lib.dll.mvd_set_view(self._ctx, i, _fp(v.image), _fp(v.weight)))
                 self.lib.check(self.lib.dll.mvd_set_psf(self._ctx, i, _fp(v.psf.psf), _i3(_xyz(v.psf.psf))))
             self.lib.check(self.lib.dll.mvd_init_views(self._ctx))       # psf.init for every view + resident spectra
             for i, v in enumerate(self.views):
@@ -313,6 +343,22 @@ class DeconViews:
         n = (C.c_longlong * 9)()
         self.lib.check(self.lib.dll.mvd_get_pass_times(self._ctx, ms, n, 1 if reset else 0))
         return [float(x) for x in ms], [int(x) for x in n]
+
+    def psi_device_ptr(self) -> int:
+        p = C.c_void_p()
+        self.lib.check(self.lib.dll.mvd_psi_device_ptr(self._ctx, C.byref(p)))
+        return int(p.value)
+
+    def stream_handle(self) -> int:
+        p = C.c_void_p()
+        self.lib.check(self.lib.dll.mvd_stream_handle(self._ctx, C.byref(p)))
+        return int(p.value or 0)
+
+    def enqueue_view_update(self, v: int):
+        self.lib.check(self.lib.dll.mvd_enqueue_view_update(self._ctx, int(v)))
+
+    def synchronize(self):
+        self.lib.check(self.lib.dll.mvd_synchronize(self._ctx))
 
     def halo_planes(self):
         lo, hi = C.c_int(), C.c_int()

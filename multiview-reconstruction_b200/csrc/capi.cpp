@@ -62,6 +62,7 @@ int mvd_create(const mvd_config* cfg, mvd_context** out) {
         c.lambda = cfg->lambda;
         c.min_value = cfg->min_value;
         c.max_len = cfg->max_fft_len > 0 ? cfg->max_fft_len : 1152;
+        c.norm_quirk_threads = cfg->norm_quirk_threads > 0 ? cfg->norm_quirk_threads : 0;
         require(cfg->psf_type >= 0 && cfg->psf_type <= 3, "bad psf_type");
         Geometry& g = c.geom;
         for (int d = 0; d < 3; ++d) {

@@ -321,8 +321,18 @@ double sum_kernel(const std::vector<float>& k) {
     for (float v : k) { double y = (double)v - c; double t = s + y; c = (t - s) - y; s = t; }
     return s;
 }
-void norm_to_sum1(std::vector<float>& k) {   // AdjustInput.normToSum1 (AdjustInput.java:52-58)
-    const double s = sum_kernel(k);
+void norm_to_sum1(std::vector<float>& k, int quirk_threads) {   // AdjustInput.normToSum1 (AdjustInput.java:52-58)
+    double s = sum_kernel(k);
+    if (quirk_threads > 0 && !k.empty()) {
+        // "Quirk A": sums[0] is added once before the loop over all portion sums (AdjustInput.java:115-119)
+        const long long size = (long long)k.size();
+        const long long T = std::max(4, quirk_threads);                                  // Threads.numThreads()
+        long long np = size <= T ? size : std::max(T, size / (64LL * 64LL * 64LL));      // FusionTools.divideIntoPortions
+        long long chunk = size / np;
+        while (chunk == 0) { --np; chunk = size / np; }
+        std::vector<float> first(k.begin(), k.begin() + chunk);
+        s += sum_kernel(first);
+    }
     for (float& v : k) v = (float)((double)v / s);
 }
 
@@ -415,7 +425,7 @@ void Engine::derive_kernels() {
     }
     for (int v = 0; v < V; ++v) {
         View& me = views_[v];
-        norm_to_sum1(me.k1);                                                                     // :125
+        norm_to_sum1(me.k1, cfg_.norm_quirk_threads);                                            // :125
         if (V == 1 || cfg_.psf_type == INDEPENDENT) {                                            // :127-131
             me.k2 = mirror_kernel(me.k1, me.k1d);
         } else if (cfg_.psf_type == EFFICIENT_BAYESIAN) {                                        // :132-195
@@ -428,7 +438,7 @@ void Engine::derive_kernels() {
                 out = conv_same(out, me.k1d, mirror_kernel(ot.k1, ot.k1d), ot.k1d);
                 for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = out[i] * tmp[i];
             }
-            norm_to_sum1(tmp);
+            norm_to_sum1(tmp, cfg_.norm_quirk_threads);
             me.k2 = tmp;
         } else if (cfg_.psf_type == OPTIMIZATION_I) {                                            // :196-242
             std::vector<float> tmp = me.k1;
@@ -438,7 +448,7 @@ void Engine::derive_kernels() {
                 std::vector<float> out = conv_same(me.k1, me.k1d, mirror_kernel(ot.k1, ot.k1d), ot.k1d);
                 for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = out[i] * tmp[i];
             }
-            norm_to_sum1(tmp);
+            norm_to_sum1(tmp, cfg_.norm_quirk_threads);
             me.k2 = mirror_kernel(tmp, me.k1d);
         } else {                                                                                 // OPTIMIZATION_II :243-253
             std::vector<float> e = me.k1;
@@ -447,7 +457,7 @@ void Engine::derive_kernels() {
                 for (int p = 1; p < V; ++p) r *= me.k1[i];       // pow by repeated float multiply (:276-284)
                 e[i] = r;
             }
-            norm_to_sum1(e);
+            norm_to_sum1(e, cfg_.norm_quirk_threads);
             me.k2 = mirror_kernel(e, me.k1d);
         }
     }

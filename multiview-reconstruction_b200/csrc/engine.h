@@ -122,6 +122,7 @@ class Engine {
         float lambda = 0.f;
         float min_value = 1e-4f;
         int max_len = 1152;
+        int norm_quirk_threads = 0;   // 0: exact kernel sums; T > 0: reproduce AdjustInput.sumImg's double count for T threads
     };
     explicit Engine(const Config& c);
     ~Engine();
@@ -191,6 +192,6 @@ class Engine {
 // helpers shared with the C ABI
 std::vector<float> mirror_kernel(const std::vector<float>& k, const int kd[3]);        // Mirror.mirror on all axes (Quirk C kept)
 double sum_kernel(const std::vector<float>& k);
-void norm_to_sum1(std::vector<float>& k);
+void norm_to_sum1(std::vector<float>& k, int quirk_threads = 0);
 
 }  // namespace mvd

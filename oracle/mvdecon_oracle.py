@@ -157,8 +157,15 @@ def compute_exponential_kernel(kernel: np.ndarray, num_views: int) -> np.ndarray
 # --------------------------------------------------------------------------------------
 def _pad_volume(img: np.ndarray, pads, ext: str, const: float) -> np.ndarray:
     if ext == "mirror":          # Views.extendMirrorSingle == numpy 'reflect'
-        # numpy reflect handles pad > n-1 by repeated reflection, like the periodic mirror strategy
-        return np.pad(img, pads, mode="reflect") if min(img.shape) > 1 else np.pad(img, pads, mode="edge")
+        # numpy reflect handles pad > n-1 by repeated reflection, like the periodic mirror strategy; a size-1 axis mirrors onto itself
+        out = img
+        for ax, pw in enumerate(pads):
+            if pw[0] == 0 and pw[1] == 0:
+                continue
+            one = [(0, 0)] * img.ndim
+            one[ax] = tuple(pw)
+            out = np.pad(out, one, mode="reflect" if out.shape[ax] > 1 else "edge")
+        return out
     if ext == "zero":
         return np.pad(img, pads, mode="constant", constant_values=0)
     if ext == "const":

@@ -1,0 +1,68 @@
+"""Golden vectors (tests/golden/small_case.npz, produced by the float64 oracle -- see make_golden.py): the float32 oracle and the
+kernel bodies (host emulation here, CUDA in test_gpu_parity.py) must reproduce them within the stated tolerance."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "small_case.npz")
+# tolerance of BASELINE.md section 6: relL2 <= max(4*eps_it, 2e-6*it), max-abs <= 1e-3 * max(psi)
+REL_TOL = lambda it: max(4 * 1.5e-7, 2e-6 * (it + 1))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def _views(o, g, ptype):
+    k = [(g[f"k1_t{ptype}_v{v}"], g[f"k2_t{ptype}_v{v}"]) for v in range(3)]
+    return [o.OracleView(g[f"img{v}"], g[f"weight{v}"], k[v][0], k[v][1], float(g["max"][v])) for v in range(3)]
+
+
+def test_oracle_float32_reproduces_golden(oracle, gold):
+    views = _views(oracle, gold, 2)
+    psi = gold["psi0"]
+    lam = float(gold["lambda"])
+    k = 0
+    for it in range(5):
+        for v in range(3):
+            psi, s, m = oracle.view_update_whole(psi, views[v], lam, dtype=np.float32)
+            if it < 2:
+                ref = gold[f"psi_it{it}_v{v}"]
+                assert oracle.rel_l2(psi, ref) <= REL_TOL(it)
+                assert np.abs(psi - ref).max() <= 1e-3 * ref.max()
+            it_, v_, s_ref, m_ref = gold["stats"][k]
+            assert abs(s - s_ref) <= 1e-4 * abs(s_ref) + 0.5 and abs(m - m_ref) <= 1e-3 * abs(m_ref) + 1e-3
+            k += 1
+    assert oracle.rel_l2(psi, gold["psi_it4"]) <= REL_TOL(4)
+
+
+def test_kernel_derivation_reproduces_golden(oracle, gold):
+    psfs = [gold[f"psf{v}"] for v in range(3)]
+    for ptype in range(4):
+        k1, k2 = oracle.derive_kernels(psfs, ptype)
+        for v in range(3):
+            assert oracle.rel_l2(k1[v], gold[f"k1_t{ptype}_v{v}"]) < 1e-6
+            assert oracle.rel_l2(k2[v], gold[f"k2_t{ptype}_v{v}"]) < 2e-6
+
+
+def test_hostemu_reproduces_golden(hostemu_lib, oracle, gold):
+    import mvrecon_b200 as m
+    views = [m.DeconView(gold[f"img{v}"], gold[f"weight{v}"], gold[f"psf{v}"], m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(3)]
+    dv = m.DeconViews(views, lambda_=float(gold["lambda"]), library=hostemu_lib)
+    try:
+        dec = m.MultiViewDeconvolutionSeq(dv, 5, m.PsiInitFromRAI(gold["psi0"], gold["max"]))
+        k = 0
+        for it in range(5):
+            for v in range(3):
+                st = (m.C.c_double * 2)()
+                assert dv.lib.dll.mvd_run_view_update(dv._ctx, v, st) == 0
+                if it < 2:
+                    assert oracle.rel_l2(dec.getPSI(), gold[f"psi_it{it}_v{v}"]) <= REL_TOL(it)
+                _, _, s_ref, m_ref = gold["stats"][k]
+                assert abs(st[0] - s_ref) <= 1e-4 * abs(s_ref) + 0.5 and abs(st[1] - m_ref) <= 1e-3 * abs(m_ref) + 1e-3
+                k += 1
+        assert oracle.rel_l2(dec.getPSI(), gold["psi_it4"]) <= REL_TOL(4)
+    finally:
+        dv.close()

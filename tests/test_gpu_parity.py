@@ -1,0 +1,324 @@
+"""GPU parity tests proper: the shipped CUDA library, called through its C ABI, against the CPU oracle on the same seeded inputs,
+against the committed golden vectors, and -- at BASELINE sizes -- through size-independent properties.
+Tolerance: relL2(gpu, float64 oracle) <= max(4*eps_it, 2e-6*it), max-abs <= 1e-3 * max(psi)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "small_case.npz")
+EPS32 = 1.5e-7
+
+
+def rel_tol(it):            # it = 1-based iteration
+    return max(4 * EPS32, 2e-6 * it)
+
+
+def _views(m, ds, ptype, n=None):
+    n = n or len(ds.psfs)
+    return [m.DeconView(ds.images[v], ds.weights[v], ds.psfs[v], m.PSFTYPE(ptype)) for v in range(n)]
+
+
+def test_library_loaded_is_the_in_tree_cuda_build(product_lib):
+    import mvrecon_b200 as m
+    assert os.path.samefile(product_lib.path, m.LIBRARY_PATH)
+    assert product_lib.getNumDevicesCUDA() >= 1
+    assert product_lib.dll.getCUDAcomputeCapabilityMajorVersion(0) == 10
+
+
+@pytest.mark.parametrize("shape,ks", [((9, 10, 11), (3, 5, 3)), ((40, 50, 70), (7, 5, 9)), ((130, 100, 90), (25, 19, 25)),
+                                      ((33, 65, 129), (4, 6, 2)), ((5, 6, 7), (7, 5, 7)), ((1, 40, 40), (1, 5, 5))])
+@pytest.mark.parametrize("ext", ["mirror", "zero", "const"])
+def test_convolve_matches_oracle(product_lib, oracle, shape, ks, ext):
+    rng = np.random.default_rng(sum(shape))
+    img = rng.random(shape).astype(np.float32)
+    k = rng.random(ks).astype(np.float32)
+    got = product_lib.convolve(img, k, ext, ext_value=1.0)
+    ref = oracle.fft_convolve(img, k, ext, const=1.0, dtype=np.float64)
+    assert oracle.rel_l2(got, ref) < 5e-7
+    assert np.abs(got - ref).max() < 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("shape", [(32, 32, 32), (64, 32, 128), (256, 256, 256), (40, 36, 60)])
+def test_legacy_convolution3DfftCUDAInPlace(product_lib, oracle, shape):
+    """L1: circular convolution, kernel centre at the origin, dims {z,y,x}  (ComputeBlockSeqThreadCUDA.java:171-208)."""
+    rng = np.random.default_rng(1)
+    img = rng.random(shape).astype(np.float32)
+    k = rng.random((5, 7, 9)).astype(np.float32)
+    ref = oracle.circular_convolve(img, k, dtype=np.float64)
+    got = img.copy()
+    product_lib.convolution3DfftCUDAInPlace(got, k, 0)
+    assert oracle.rel_l2(got, ref) < 5e-7
+
+
+def test_legacy_out_of_place_and_device_queries(product_lib, oracle):
+    rng = np.random.default_rng(2)
+    img = rng.random((32, 40, 48)).astype(np.float32)
+    k = rng.random((3, 3, 5)).astype(np.float32)
+    imd, kd = (C.c_int * 3)(*img.shape), (C.c_int * 3)(*k.shape)
+    ptr = product_lib.dll.convolution3DfftCUDA(img.ctypes.data_as(C.POINTER(C.c_float)), imd, k.ctypes.data_as(C.POINTER(C.c_float)), kd, 0)
+    assert ptr
+    got = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=img.shape).copy()
+    C.CDLL(None).free(C.c_void_p(ptr))
+    assert oracle.rel_l2(got, oracle.circular_convolve(img, k, dtype=np.float64)) < 5e-7
+    assert "B200" in product_lib.getNameDeviceCUDA(0) or len(product_lib.getNameDeviceCUDA(0)) > 0
+    assert product_lib.dll.getFreeMemDeviceCUDA(0) > 0
+
+
+@pytest.mark.parametrize("ptype", [0, 1, 2, 3])
+@pytest.mark.parametrize("lam", [0.0, 0.006])
+def test_loop_parity_per_iteration(product_lib, oracle, small_dataset, ptype, lam):
+    import mvrecon_b200 as m
+    ds = small_dataset
+    views, psi0, avg = oracle.make_oracle_views(ds, ptype)
+    dv = m.DeconViews(_views(m, ds, ptype), lambda_=lam)
+    try:
+        for v in range(3):
+            assert oracle.rel_l2(dv.views[v].psf.getKernel1(), views[v].kernel1) < 1e-6
+            assert oracle.rel_l2(dv.views[v].psf.getKernel2(), views[v].kernel2) < 2e-6
+        dec = m.MultiViewDeconvolutionSeq(dv, 10, m.PsiInitFromRAI(psi0, [v.max_intensity for v in views]))
+        psi64 = psi0
+        for it in range(1, 11):
+            stats = dec.runNextIteration()
+            for v in range(3):
+                psi64, s, mx = oracle.view_update_whole(psi64, views[v], lam, dtype=np.float64)
+                assert abs(stats[v].sumChange - s) <= 2e-4 * abs(s) + 1.0
+                assert abs(stats[v].maxChange - mx) <= 2e-3 * abs(mx) + 1e-3
+            psi = dec.getPSI()
+            assert oracle.rel_l2(psi, psi64) <= rel_tol(it), it
+            assert np.abs(psi - psi64).max() <= 1e-3 * psi64.max()
+    finally:
+        dv.close()
+
+
+def test_golden_vectors(product_lib, oracle):
+    import mvrecon_b200 as m
+    gold = np.load(GOLD)
+    views = [m.DeconView(gold[f"img{v}"], gold[f"weight{v}"], gold[f"psf{v}"], m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(3)]
+    dv = m.DeconViews(views, lambda_=float(gold["lambda"]))
+    try:
+        for ptype in (2,):
+            for v in range(3):
+                assert oracle.rel_l2(dv.views[v].psf.getKernel1(), gold[f"k1_t{ptype}_v{v}"]) < 1e-6
+                assert oracle.rel_l2(dv.views[v].psf.getKernel2(), gold[f"k2_t{ptype}_v{v}"]) < 2e-6
+        dec = m.MultiViewDeconvolutionSeq(dv, 5, m.PsiInitFromRAI(gold["psi0"], gold["max"]))
+        k = 0
+        for it in range(5):
+            for v in range(3):
+                st = (C.c_double * 2)()
+                assert dv.lib.dll.mvd_run_view_update(dv._ctx, v, st) == 0
+                if it < 2:
+                    assert oracle.rel_l2(dec.getPSI(), gold[f"psi_it{it}_v{v}"]) <= rel_tol(it + 1)
+                _, _, s_ref, m_ref = gold["stats"][k]
+                assert abs(st[0] - s_ref) <= 2e-4 * abs(s_ref) + 0.5 and abs(st[1] - m_ref) <= 2e-3 * abs(m_ref) + 1e-3
+                k += 1
+        assert oracle.rel_l2(dec.getPSI(), gold["psi_it4"]) <= rel_tol(5)
+    finally:
+        dv.close()
+
+
+@pytest.mark.parametrize("ptype", [0, 1, 2, 3])
+def test_golden_kernels_all_psf_types(product_lib, oracle, ptype):
+    import mvrecon_b200 as m
+    gold = np.load(GOLD)
+    views = [m.DeconView(gold[f"img{v}"], gold[f"weight{v}"], gold[f"psf{v}"], m.PSFTYPE(ptype)) for v in range(3)]
+    dv = m.DeconViews(views)
+    try:
+        for v in range(3):
+            assert oracle.rel_l2(dv.views[v].psf.getKernel1(), gold[f"k1_t{ptype}_v{v}"]) < 1e-6
+            assert oracle.rel_l2(dv.views[v].psf.getKernel2(), gold[f"k2_t{ptype}_v{v}"]) < 2e-6
+    finally:
+        dv.close()
+
+
+def test_norm_quirk_switch(product_lib, oracle, small_dataset):
+    import mvrecon_b200 as m
+    views, psi0, avg = oracle.make_oracle_views(small_dataset, oracle.EFFICIENT_BAYESIAN, quirk_threads=8)
+    dv = m.DeconViews(_views(m, small_dataset, 2), lambda_=0.006, norm_quirk_threads=8)
+    try:
+        dec = m.MultiViewDeconvolutionSeq(dv, 3, m.PsiInitFromRAI(psi0, [v.max_intensity for v in views]))
+        dec.runIterations()
+        ref, _ = oracle.run_iterations_seq(psi0, views, 3, 0.006, dtype=np.float64)
+        assert oracle.rel_l2(dec.getPSI(), ref) <= rel_tol(3)
+    finally:
+        dv.close()
+
+
+@pytest.mark.parametrize("max_len", [40, 48, 64, 0])
+def test_tiling_independence(product_lib, oracle, max_len):
+    """halo'd multi-tile plans reproduce the whole-volume result (MultiViewDeconvolutionSeq's blocks == whole volume)."""
+    import mvrecon_b200 as m
+    ds = oracle.make_synthetic((70, 90, 100), 2, seed=2, psf_size_xyz=(9, 7, 9), psf_sigma_xyz=(1.5, 1.2, 2.5), bead_density=2048)
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN)
+    dv = m.DeconViews(_views(m, ds, 2), max_fft_len=max_len)
+    try:
+        dec = m.MultiViewDeconvolutionSeq(dv, 2, m.PsiInitFromRAI(psi0, [v.max_intensity for v in views]))
+        dec.runIterations()
+        psi = dec.getPSI()
+        info = dv.tile_info()
+    finally:
+        dv.close()
+    ref, _ = oracle.run_iterations_seq(psi0, views, 2, 0.0, dtype=np.float64)
+    assert oracle.rel_l2(psi, ref) <= rel_tol(2), info
+
+
+def test_block_operator_and_blocked_driver(product_lib, oracle, small_dataset):
+    """L2: ComputeBlockSeqThread.runIteration on halo'd blocks, driven like MultiViewDeconvolutionSeq.runNextIteration."""
+    import mvrecon_b200 as m
+    ds = small_dataset
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.INDEPENDENT)
+    mx = [v.max_intensity for v in views]
+    fac = m.ComputeBlockSeqThreadB200Factory(1e-4, 0.006, (32, 32, 32), devices=(0,))
+    assert fac.numParallelBlocks() == 1
+    psi = psi0.copy()
+    mv = [m.DeconView(ds.images[v], ds.weights[v], ds.psfs[v]) for v in range(3)]
+    stats = m.runNextIterationBlocked(psi, mv, [(v.kernel1, v.kernel2) for v in views], mx, fac)
+    ref, st = oracle.run_iterations_seq(psi0, views, 1, 0.006, dtype=np.float64)
+    refb, stb = oracle.run_iterations_seq(psi0, views, 1, 0.006, dtype=np.float64, block_size_xyz=(32, 32, 32))
+    assert oracle.rel_l2(psi, ref) <= rel_tol(1)
+    for v in range(3):      # block statistics include the halo, exactly like the reference (ComputeBlockSeqThreadCPU.java:129-157)
+        assert abs(stats[v].sumChange - stb[v][2]) <= 2e-4 * abs(stb[v][2]) + 1.0
+
+
+def test_sharded_contexts_equal_single_context(product_lib, oracle):
+    import mvrecon_b200 as m
+    ds = oracle.make_synthetic((64, 36, 40), 2, seed=3, psf_size_xyz=(5, 5, 7), psf_sigma_xyz=(1.0, 1.0, 1.6), bead_density=1024)
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN)
+    mx = [v.max_intensity for v in views]
+    nz, H = 64, 6
+    shards = []
+    for lo, hi in [(0, 20), (20, 47), (47, 64)]:
+        z0, z1 = max(0, lo - H), min(nz, hi + H)
+        loc = [m.DeconView(ds.images[v][z0:z1], ds.weights[v][z0:z1], ds.psfs[v], m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(2)]
+        d = m.DeconViews(loc, shard=(lo, hi, z0, z1 - z0), global_dims_zyx=(nz, 36, 40))
+        shards.append((d, m.MultiViewDeconvolutionSeq(d, 0, m.PsiInitFromRAI(psi0[z0:z1], mx)), lo, hi, z0, z1))
+    full = psi0.copy()
+    psi64 = psi0
+    for it in range(2):
+        for v in range(2):
+            new = np.empty_like(full)
+            for d, dec, lo, hi, z0, z1 in shards:
+                d.enqueue_view_update(v)
+                d.synchronize()
+                new[lo:hi] = dec.getPSI()[lo - z0:hi - z0]
+            full = new
+            psi64, _, _ = oracle.view_update_whole(psi64, views[v], 0.0, dtype=np.float64)
+            assert oracle.rel_l2(full, psi64) <= rel_tol(it + 1)
+            for d, dec, lo, hi, z0, z1 in shards:
+                assert d.lib.dll.mvd_set_psi(d._ctx, np.ascontiguousarray(full[z0:z1]).ctypes.data_as(m._F)) == 0
+    for d, *_ in shards:
+        d.close()
+
+
+def test_edge_cases(product_lib, oracle):
+    import mvrecon_b200 as m
+    rng = np.random.default_rng(5)
+    # single view falls back to the flipped kernel; weight 0 leaves psi bit-exact; img == 0 -> quotient 1
+    shape = (20, 24, 28)
+    psf = oracle.synth_psf(0, 1, (5, 5, 5), (1.0, 1.0, 1.0))
+    img = (50 + 10 * rng.random(shape)).astype(np.float32)
+    img[:, :, :5] = 0
+    w = np.ones(shape, np.float32)
+    w[:6] = 0
+    psi0 = (40 + rng.random(shape)).astype(np.float32)
+    dv = m.DeconViews([m.DeconView(img, w, psf, m.PSFTYPE.EFFICIENT_BAYESIAN)])
+    try:
+        k1, k2 = dv.views[0].psf.getKernel1(), dv.views[0].psf.getKernel2()
+        assert np.array_equal(k2, k1[::-1, ::-1, ::-1])
+        dec = m.MultiViewDeconvolutionSeq(dv, 1, m.PsiInitFromRAI(psi0, [60.0]))
+        dec.runIterations()
+        psi = dec.getPSI()
+    finally:
+        dv.close()
+    assert np.array_equal(psi[:6], psi0[:6])
+    ref, _, _ = oracle.view_update_whole(psi0, oracle.OracleView(img, w, k1, k2, 60.0), 0.0, dtype=np.float64)
+    assert oracle.rel_l2(psi, ref) <= rel_tol(1)
+    # value <= 0 / NaN -> minValue: psi with zeros and an image that makes the blur vanish
+    psiz = np.zeros(shape, np.float32)
+    dv = m.DeconViews([m.DeconView(img, np.ones(shape, np.float32), psf)])
+    try:
+        dec = m.MultiViewDeconvolutionSeq(dv, 1, m.PsiInitFromRAI(psiz, [60.0]))
+        dec.runIterations()
+        out = dec.getPSI()
+    finally:
+        dv.close()
+    assert np.all(out == np.float32(1e-4))
+    # errors surface as exceptions with a message, never as silent fallbacks
+    with pytest.raises(m.MvdError):
+        m.DeconViews([m.DeconView(img, w, psf), m.DeconView(img[:-1], w[:-1], psf)])
+    with pytest.raises(m.MvdError):
+        m.DeconViews([m.DeconView(img, w, np.ones((5, 5, 2000), np.float32))])        # PSF larger than any FFT tile
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE-size properties (config c2: 512 x 512 x 256): size-independent invariants instead of a CPU recomputation
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c2_volume():
+    rng = np.random.default_rng(11)
+    return (100 + 50 * rng.random((256, 512, 512), dtype=np.float32)).astype(np.float32)
+
+
+def test_fullsize_convolution_linearity_and_mass(product_lib, oracle, c2_volume):
+    psf = oracle.synth_psf(1, 6)
+    a = c2_volume
+    b = np.roll(a, 7, axis=2)
+    ca, cb = product_lib.convolve(a, psf, "mirror"), product_lib.convolve(b, psf, "mirror")
+    cab = product_lib.convolve((2 * a + 3 * b).astype(np.float32), psf, "mirror")
+    assert oracle.rel_l2(cab, 2 * ca.astype(np.float64) + 3 * cb) < 1e-6
+    const = np.full(a.shape, 7.0, np.float32)
+    assert np.abs(product_lib.convolve(const, psf, "mirror") - 7.0).max() < 5e-5           # sum K = 1
+    # zero extension conserves mass: sum(out) over an enlarged support == sum(in) * sum(K); check the interior identity instead
+    delta = np.zeros((3, 3, 3), np.float32)
+    delta[1, 1, 1] = 1
+    assert np.array_equal(product_lib.convolve(a, delta, "mirror"), a) or oracle.rel_l2(product_lib.convolve(a, delta, "mirror"), a) < 3e-7
+
+
+def test_fullsize_update_properties(product_lib, oracle, c2_volume):
+    """6-view 512x512x256 EB + Tikhonov (config c2): determinism, weight-0 invariance, agreement with the oracle on a sub-block."""
+    import mvrecon_b200 as m
+    V = 3                                             # three of the six views keep host memory modest
+    psfs = [oracle.synth_psf(v, 6) for v in range(V)]
+    img = c2_volume
+    w = np.full(img.shape, 1.0 / V, np.float32)
+    w[:, :, 300:] = 0
+    views = [m.DeconView(np.roll(img, 3 * v, axis=1), w, psfs[v], m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(V)]
+    outs = []
+    for rep in range(2):
+        dv = m.DeconViews(views, lambda_=0.006)
+        try:
+            dec = m.MultiViewDeconvolutionSeq(dv, 1, m.PsiInitFromRAI(img, [200.0] * V))
+            dec.runIterations()
+            outs.append(dec.getPSI())
+            k = [(dv.views[v].psf.getKernel1(), dv.views[v].psf.getKernel2()) for v in range(V)]
+        finally:
+            dv.close()
+    assert np.array_equal(outs[0], outs[1])                                     # bitwise deterministic
+    assert np.array_equal(outs[0][:, :, 300:], img[:, :, 300:])                 # weight 0 => untouched
+    assert np.isfinite(outs[0]).all()
+    # oracle on a sub-block far from the volume faces: the halo makes the crop exact (block independence)
+    z, y, x, s, h = 100, 200, 100, 48, 30
+    sl = (slice(z - h, z + s + h), slice(y - h, y + s + h), slice(x - h, x + s + h))
+    psi = img[sl].astype(np.float32)
+    for v in range(V):
+        ov = oracle.OracleView(np.roll(img, 3 * v, axis=1)[sl], w[sl], k[v][0], k[v][1], 200.0)
+        nxt, _, _ = oracle.view_update_whole(psi, ov, 0.006, dtype=np.float64)
+        # only the centre of the crop is valid after each view update; shrink the trusted region by the kernel reach
+        psi = nxt
+    core = (slice(h, h + s),) * 3
+    got = outs[0][z:z + s, y:y + s, x:x + s]
+    # after 3 view updates the crop is contaminated up to 3*(k-1) = 72 voxels from its faces in z/x; compare one update only
+    dv = m.DeconViews(views[:1], lambda_=0.006)
+    try:
+        dec = m.MultiViewDeconvolutionSeq(dv, 1, m.PsiInitFromRAI(img, [200.0]))
+        dec.runIterations()
+        one = dec.getPSI()
+        k1, k2 = dv.views[0].psf.getKernel1(), dv.views[0].psf.getKernel2()
+    finally:
+        dv.close()
+    ov = oracle.OracleView(img[sl], w[sl], k1, k2, 200.0)
+    ref, _, _ = oracle.view_update_whole(img[sl], ov, 0.006, dtype=np.float64)
+    assert oracle.rel_l2(one[z:z + s, y:y + s, x:x + s], ref[core]) <= rel_tol(1)
+    assert got.shape == (s, s, s)

@@ -55,6 +55,21 @@ def test_loop_parity_all_psf_types(hostemu_lib, oracle, small_dataset, ptype):
         assert abs(got.maxChange - mx) <= 1e-3 * max(abs(mx), 1.0)
 
 
+def test_norm_quirk_switch_matches_oracle(hostemu_lib, oracle, small_dataset):
+    """mvd_config.norm_quirk_threads reproduces AdjustInput.sumImg's double count exactly like the oracle's switch."""
+    import mvrecon_b200 as m
+    ds = small_dataset
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN, quirk_threads=8)
+    dv = m.DeconViews(_views(m, ds, 2), norm_quirk_threads=8, library=hostemu_lib)
+    try:
+        for v in range(3):
+            assert abs(float(dv.views[v].psf.getKernel1().sum(dtype=np.float64)) - float(views[v].kernel1.sum(dtype=np.float64))) < 1e-6
+            assert oracle.rel_l2(dv.views[v].psf.getKernel1(), views[v].kernel1) < 1e-6
+            assert oracle.rel_l2(dv.views[v].psf.getKernel2(), views[v].kernel2) < 2e-6
+    finally:
+        dv.close()
+
+
 def test_multitile_equals_single_tile(hostemu_lib, oracle):
     """several halo'd tiles per axis (max_fft_len forces tiling) give the whole-volume result."""
     import mvrecon_b200 as m

@@ -1,0 +1,70 @@
+"""N > 1 path on CPU: two processes (gloo) each own a z-slab, run the view updates through the host-emulated kernel bodies and
+exchange psi halos with mvrecon_b200.sharding.exchange_halos -- the same function bench.py uses with NCCL on the GPUs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DIMS, VIEWS = (48, 20, 24), 2
+KW = dict(psf_size_xyz=(5, 3, 5), psf_sigma_xyz=(1.0, 0.8, 1.4), bead_density=512)
+
+
+def _worker(rank, world, port, lib_path, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import torch.distributed as dist
+    import mvdecon_oracle as o
+    import mvrecon_b200 as m
+    from mvrecon_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = m.Lib(lib_path)
+    ds = o.make_synthetic(DIMS, VIEWS, seed=5, **KW)
+    views, psi0, avg = o.make_oracle_views(ds, o.EFFICIENT_BAYESIAN)
+    nz, ny, nx = DIMS
+    H = KW["psf_size_xyz"][2] - 1
+    lo, hi = sharding.slab_range(nz, world, rank)
+    z0, z1 = sharding.extended_range(lo, hi, nz, H)
+    loc = [m.DeconView(ds.images[v][z0:z1], ds.weights[v][z0:z1], ds.psfs[v], m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(VIEWS)]
+    dv = m.DeconViews(loc, shard=(lo, hi, z0, z1 - z0), global_dims_zyx=DIMS, library=lib)
+    assert dv.halo_planes() == ((0 if rank == 0 else H), (0 if rank == world - 1 else H))
+    dec = m.MultiViewDeconvolutionSeq(dv, 0, m.PsiInitFromRAI(psi0[z0:z1], [v.max_intensity for v in views]))
+    plane = ny * nx
+    for it in range(2):
+        for v in range(VIEWS):
+            dv.enqueue_view_update(v)
+            dv.synchronize()
+            buf = torch.from_numpy(dec.getPSI().reshape(-1).copy())
+            sharding.exchange_halos(buf, plane, lo, hi, z0, H, rank, world, dist)
+            assert lib.dll.mvd_set_psi(dv._ctx, buf.numpy().ctypes.data_as(m._F)) == 0
+    np.save(os.path.join(out_dir, f"slab{rank}.npy"), dec.getPSI()[lo - z0:hi - z0])
+    dv.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_z_sharding_with_gloo_halo_exchange(hostemu_lib, oracle, tmp_path):
+    import torch.multiprocessing as mp
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.start_processes(_worker, args=(world, port, hostemu_lib.path, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    ds = oracle.make_synthetic(DIMS, VIEWS, seed=5, **KW)
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN)
+    ref, _ = oracle.run_iterations_seq(psi0, views, 2, 0.0, dtype=np.float64)
+    got = np.concatenate([np.load(tmp_path / f"slab{r}.npy") for r in range(world)], axis=0)
+    assert got.shape == ref.shape
+    assert oracle.rel_l2(got, ref) < 4e-6
+
+
+def test_slab_ranges_cover_the_volume():
+    sys.path.insert(0, ROOT)
+    from mvrecon_b200 import sharding
+    for nz, world in [(512, 8), (100, 3), (7, 7)]:
+        r = [sharding.slab_range(nz, world, k) for k in range(world)]
+        assert r[0][0] == 0 and r[-1][1] == nz and all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+    assert sharding.extended_range(64, 128, 512, 24) == (40, 152)
+    assert sharding.extended_range(0, 64, 512, 24) == (0, 88)
