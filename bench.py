@@ -360,6 +360,14 @@ def run_ours(args):
 
     # ---------------- e2e leg: public host API, host buffers, copies inside the timed region --------------------
     e2e_iters = args.e2e_iterations
+    if args.skip_e2e:
+        if rank == 0:
+            print(json.dumps({"metric": "voxel*view*iterations/s", "value": value, "n_gpus": world, "ms_per_step": ms / args.steps,
+                              "note": "profiling run (--skip-e2e): not a bench line",
+                              "all_passes_ms_per_launch": [round(a / max(b, 1), 4) for a, b in zip(pass_ms, pass_n)]}))
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
     host = []
     for im, w in zip(imgs, weights):
         hi_, hw_ = torch.empty(im.shape, dtype=torch.float32, pin_memory=True), torch.empty(w.shape, dtype=torch.float32, pin_memory=True)
@@ -397,7 +405,7 @@ def run_ours(args):
         useful_vox_per_launch = (hi - lo) * plane / info["num_tiles"]
         achieved = PASS_BYTES[dom] * useful_vox_per_launch / (per_launch_ms * 1e-3) / 1e9
         cpu = None
-        if world == 1:
+        if world == 1 and not args.skip_cpu:
             o, views, cpsi, clam, sdims = cpu_sample_setup(name)
             cores = os.cpu_count() or 1
             cpsi, _ = o.run_iterations_seq(cpsi, views, 1, clam, dtype=np.float32)      # warm-up (plans, page faults)
@@ -440,6 +448,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-iterations", type=int, default=10)
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: kernel-only leg only")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: no CPU baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

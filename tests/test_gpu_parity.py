@@ -249,7 +249,7 @@ def test_edge_cases(product_lib, oracle):
     with pytest.raises(m.MvdError):
         m.DeconViews([m.DeconView(img, w, psf), m.DeconView(img[:-1], w[:-1], psf)])
     with pytest.raises(m.MvdError):
-        m.DeconViews([m.DeconView(img, w, np.ones((5, 5, 2000), np.float32))])        # PSF larger than any FFT tile
+        m.DeconViews([m.DeconView(img, w, np.ones((5, 5, 5000), np.float32))])        # PSF larger than any FFT tile
 
 
 # ---------------------------------------------------------------------------------------------------------------------
