@@ -132,7 +132,10 @@ struct ReduceParts2 {
 // ------------------------------------------------------------------------------------------------
 Convolver::Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], int xmode, int max_len, stream_t s, Tables* tables)
     : g_(g), xmode_(xmode), stream_(s), tables_(tables) {
-    if (const char* e = std::getenv("MVD_PREFETCH_DIST")) pf_dist_ = std::atoi(e);
+    if (const char* e = std::getenv("MVD_PREFETCH_DIST")) pf_x_ = pf_y_ = pf_z_ = std::atoi(e);
+    if (const char* e = std::getenv("MVD_PF_X")) pf_x_ = std::atoi(e);
+    if (const char* e = std::getenv("MVD_PF_Y")) pf_y_ = std::atoi(e);
+    if (const char* e = std::getenv("MVD_PF_Z")) pf_z_ = std::atoi(e);
     AxisTiling ax[3];
     if (xmode == 1) {
         for (int d = 0; d < 3; ++d) {
@@ -195,8 +198,10 @@ XArgs Convolver::base_xargs(const TileGeom& t) const {
     a.ext_value = 0.f;
     a.min_value = 1e-4f;
     a.max_intensity = 1.f;
-    a.pf_dist = pf_dist_;
+    a.pf_dist = pf_x_;
     a.nblocks = xblocks_;
+    // one reflection suffices when the tile never reaches further than gdim-1 beyond either face of the volume
+    a.xsimple = (t.org[0] >= -(g_.gdim[0] - 1) && t.org[0] + T_[0] - 1 <= 2 * g_.gdim[0] - 2) ? 1 : 0;
     return a;
 }
 
@@ -212,7 +217,7 @@ void Convolver::col(int axis, int mode, const cpx* khat) {
     else { c.stride_n = (long long)px_ * T_[1]; c.stride_b = px_; gy = T_[1]; }
     c.gx = (M_ + o->W - 1) / o->W;
     c.gy = gy;
-    c.pf_dist = pf_dist_;
+    c.pf_dist = axis == 1 ? pf_y_ : pf_z_;
     o->launch_col(mode, c, c.gx, gy, stream_);
 }
 

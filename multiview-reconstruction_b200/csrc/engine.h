@@ -92,7 +92,8 @@ class Convolver {
     Tables* tables_;
     cpx* work_ = nullptr;
     float* kpad_ = nullptr;
-    int pf_dist_ = 148;    // software L2 prefetch distance in CTAs (one CTA per SM ahead; MVD_PREFETCH_DIST overrides)
+    // software L2 prefetch distance in CTAs for the x, y and z passes (MVD_PF_X / MVD_PF_Y / MVD_PF_Z override)
+    int pf_x_ = 74, pf_y_ = 296, pf_z_ = 148;
     // profiling
     void mark(int pass);
     bool prof_on_ = false;

@@ -301,10 +301,12 @@ template <int N, int BLK, int R, class Src, class Dst, class Khat>
 MVD_HD void stage_conv(int g, Src&& src, Dst&& dst, Khat&& khat) {
     static_assert(BLK == R, "stage_conv is the last forward stage");
     const int base = g * BLK;
-    cpx a[R];
+    cpx a[R], kh[R];
+    // the kernel-spectrum loads go out first: their (L2 / DRAM) latency overlaps the shared-memory reads and the forward DFT
+    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; kh[p] = khat(base + p); });
     static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; a[p] = src(base + p); });
     Dft<R, 0, 1, false, R>::run(a);
-    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; a[p] = cmul(a[p], khat(base + p)); });
+    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; a[p] = cmul(a[p], kh[p]); });
     Dft<R, 0, 1, true, R>::run(a);
     static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; dst(base + p, a[p]); });
 }

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(P::XTHREADS, x_min_blocks<P>()) x_kernel(const
     extern __shared__ __align__(16) unsigned char mvd_smem[];
     DevExec ex;
     cpx* sm = reinterpret_cast<cpx*>(mvd_smem);
-    LineInfo* li = reinterpret_cast<LineInfo*>(sm + XLay<P>::TILE + XLay<P>::NTW);
+    LineInfo* li = reinterpret_cast<LineInfo*>(sm + XLay<P>::TILE + XLay<P>::NTAB);
     x_pass_body<P, KIND>(ex, a, (int)blockIdx.x, sm, li);
 }
 #endif
@@ -71,7 +71,7 @@ struct LenImpl {
         (void)s;
         std::vector<unsigned char> raw(smem_x + 16);
         cpx* sm = reinterpret_cast<cpx*>(raw.data());
-        LineInfo* li = reinterpret_cast<LineInfo*>(sm + XLay<P>::TILE + XLay<P>::NTW);
+        LineInfo* li = reinterpret_cast<LineInfo*>(sm + XLay<P>::TILE + XLay<P>::NTAB);
         HostExec ex(P::XTHREADS);
         for (int bx = 0; bx < nblocks; ++bx) x_pass_body<P, KIND>(ex, a, bx, sm, li);
 #else
