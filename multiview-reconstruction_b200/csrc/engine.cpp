@@ -110,6 +110,10 @@ struct PlaceKernel {   // scatter the (tiny) kernel into a zeroed tile with its 
         out[((long long)pz * T1 + py) * T0 + px] = s * k[i];
     }
 };
+struct FillParts {      // unused partial-statistics slots must read as {0, -1}
+    double* ps; float* pm;
+    MVD_HD void operator()(long long i) const { ps[i] = 0.0; pm[i] = -1.f; }
+};
 struct ReduceParts1 {
     const double* ps; const float* pm; int n; double* ts; float* tm;
     MVD_HD void operator()(long long lane) const {
@@ -154,7 +158,14 @@ Convolver::Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], in
     oz_ = find_len_ops(T_[2]);
     if (!ox_ || !oy_ || !oz_) throw Error("internal: planned length without kernels");
     px_ = (M_ + 15) / 16 * 16;                            // 128-byte rows: every 16-column segment is one cache line
-    xblocks_ = (T_[1] * T_[2] + ox_->XL - 1) / ox_->XL;
+    xblocks_ = (T_[1] * T_[2] + ox_->XL - 1) / ox_->XL + T_[2];      // partial-statistics slots per tile (chunked launches included)
+    {
+        double mb = 0.0;      // MVD_CHUNK_MB: plane-chunk size (MB) of the x/y chains; measured slower than whole-tile launches on B200 -> off
+        if (const char* e = std::getenv("MVD_CHUNK_MB")) mb = std::atof(e);
+        const double plane_mb = (double)px_ * T_[1] * sizeof(cpx) / 1.0e6;
+        chunk_planes_ = mb > 0 ? std::max(1, (int)(mb / plane_mb)) : 0;
+        if (chunk_planes_ >= T_[2]) chunk_planes_ = 0;
+    }
     for (const AxisTile& tz : ax[2].tiles)
         for (const AxisTile& ty : ax[1].tiles)
             for (const AxisTile& tx : ax[0].tiles) {
@@ -205,7 +216,17 @@ XArgs Convolver::base_xargs(const TileGeom& t) const {
     return a;
 }
 
-void Convolver::col(int axis, int mode, const cpx* khat) {
+void Convolver::xpass(int kind, XArgs a, int z0, int z1) {
+    if (z1 < 0) z1 = T_[2];
+    a.line0 = z0 * T_[1];
+    a.line_end = z1 * T_[1];
+    const int nb = (a.line_end - a.line0 + ox_->XL - 1) / ox_->XL;
+    a.nblocks = nb;
+    if (a.part_sum) { a.part_sum += (size_t)(a.line0 / ox_->XL) + (size_t)z0; a.part_max += (size_t)(a.line0 / ox_->XL) + (size_t)z0; }
+    ox_->launch_x(kind, a, nb, stream_);
+}
+
+void Convolver::col(int axis, int mode, const cpx* khat, int z0, int z1) {
     ColArgs c;
     c.data = work_;
     c.khat = khat;
@@ -213,7 +234,11 @@ void Convolver::col(int axis, int mode, const cpx* khat) {
     const LenOps* o = axis == 1 ? oy_ : oz_;
     c.tw = tables_->tw(o->N);
     int gy;
-    if (axis == 1) { c.stride_n = px_; c.stride_b = (long long)px_ * T_[1]; gy = T_[2]; }
+    if (axis == 1) {                                     // y pass: one CTA row per z plane; plane chunks [z0, z1)
+        if (z1 < 0) z1 = T_[2];
+        c.stride_n = px_; c.stride_b = (long long)px_ * T_[1]; gy = z1 - z0;
+        c.data = work_ + (size_t)z0 * c.stride_b;
+    }
     else { c.stride_n = (long long)px_ * T_[1]; c.stride_b = px_; gy = T_[1]; }
     c.gx = (M_ + o->W - 1) / o->W;
     c.gy = gy;
@@ -240,7 +265,7 @@ cpx* Convolver::build_khat(const float* kernel_host, const int kd[3]) {
     for (int d = 0; d < 3; ++d) { a.vol[d] = T_[d]; a.gdim[d] = T_[d]; a.goff[d] = 0; }
     a.src = kpad_;
     a.ext = EXT_ZERO;
-    ox_->launch_x(X_FWD, a, xblocks_, stream_);
+    xpass(X_FWD, a);
     col(1, COL_FWD, nullptr);
     col(2, COL_FWD, nullptr);
     cpx* khat = (cpx*)dev::alloc(sizeof(cpx) * tile_elems());
@@ -256,31 +281,39 @@ void Convolver::conv(const float* src, float* dst, const cpx* khat, int ext, flo
         a.src = src;
         a.ext = ext;
         a.ext_value = ext_value;
-        ox_->launch_x(X_FWD, a, xblocks_, stream_);
+        xpass(X_FWD, a);
         col(1, COL_FWD, nullptr);
         col(2, COL_CONV, khat);
         col(1, COL_INV, nullptr);
         a.dst = dst;
-        ox_->launch_x(X_INV, a, xblocks_, stream_);
+        xpass(X_INV, a);
     }
 }
 
 void Convolver::view_update(const float* psi_in, float* psi_out, const float* img, const float* weight, const cpx* k1hat,
                             const cpx* k2hat, float lambda, float min_value, float max_intensity, double* part_sum, float* part_max) {
     int ti = 0;
+    const int cp = chunk_planes_ > 0 ? chunk_planes_ : T_[2];
     for (const TileGeom& t : tiles_) {
         XArgs a = base_xargs(t);
-        a.src = psi_in;                                   // P1: mirror-single outside the volume (MultiViewDeconvolutionSeq.java:115)
-        a.ext = EXT_MIRROR;
-        mark(0); ox_->launch_x(X_FWD, a, xblocks_, stream_);
-        mark(1); col(1, COL_FWD, nullptr);                // P2
+        // x/y pass chains run plane chunk by plane chunk so that the hand-over P1->P2, P4->P5->P6, P8->P9 stays in the 126 MB L2;
+        // the z passes (P3, P7) need every plane and run over the whole tile.
+        for (int z0 = 0; z0 < T_[2]; z0 += cp) {
+            const int z1 = std::min(T_[2], z0 + cp);
+            a.src = psi_in;                               // P1: mirror-single outside the volume (MultiViewDeconvolutionSeq.java:115)
+            a.ext = EXT_MIRROR;
+            mark(0); xpass(X_FWD, a, z0, z1);
+            mark(1); col(1, COL_FWD, nullptr, z0, z1);    // P2
+        }
         mark(2); col(2, COL_CONV, k1hat);                 // P3
-        mark(3); col(1, COL_INV, nullptr);                // P4
-        a.src = img;                                      // P5: quotient, 1 where there is no image data
-        mark(4); ox_->launch_x(X_RATIO, a, xblocks_, stream_);
-        mark(5); col(1, COL_FWD, nullptr);                // P6
+        for (int z0 = 0; z0 < T_[2]; z0 += cp) {
+            const int z1 = std::min(T_[2], z0 + cp);
+            mark(3); col(1, COL_INV, nullptr, z0, z1);    // P4
+            a.src = img;                                  // P5: quotient, 1 where there is no image data
+            mark(4); xpass(X_RATIO, a, z0, z1);
+            mark(5); col(1, COL_FWD, nullptr, z0, z1);    // P6
+        }
         mark(6); col(2, COL_CONV, k2hat);                 // P7
-        mark(7); col(1, COL_INV, nullptr);                // P8
         a.src = psi_in;                                   // P9
         a.weight = weight;
         a.dst = psi_out;
@@ -289,7 +322,11 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
         a.max_intensity = max_intensity;
         a.part_sum = part_sum + (size_t)ti * xblocks_;
         a.part_max = part_max + (size_t)ti * xblocks_;
-        mark(8); ox_->launch_x(X_UPDATE, a, xblocks_, stream_);
+        for (int z0 = 0; z0 < T_[2]; z0 += cp) {
+            const int z1 = std::min(T_[2], z0 + cp);
+            mark(7); col(1, COL_INV, nullptr, z0, z1);    // P8
+            mark(8); xpass(X_UPDATE, a, z0, z1);
+        }
         mark(-1);
         ++ti;
     }
@@ -494,6 +531,7 @@ void Engine::init_views() {
     dev::free_(part_sum_); dev::free_(part_max_);
     part_sum_ = (double*)dev::alloc(sizeof(double) * (nparts + 256));
     part_max_ = (float*)dev::alloc(sizeof(float) * (nparts + 256));
+    pfor((long long)nparts + 256, FillParts{part_sum_, part_max_}, stream_);
     inited_ = true;
 }
 

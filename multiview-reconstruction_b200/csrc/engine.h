@@ -64,7 +64,10 @@ class Convolver {
     const int* tile_dims() const { return T_; }                                   // {Tx(real), Ty, Tz}
     const std::vector<TileGeom>& tiles() const { return tiles_; }
     double fft_volume_ratio() const;                                              // FFT-box voxels / useful voxels
-    int launches_per_update() const { return 9 * num_tiles(); }
+    int launches_per_update() const {
+        const int chunks = chunk_planes_ > 0 ? (T_[2] + chunk_planes_ - 1) / chunk_planes_ : 1;
+        return (7 * chunks + 2) * num_tiles();
+    }
 
     // kernel (x fastest, dims kd) -> resident spectrum (scale 1/Nfft folded in); caller owns the buffer
     cpx* build_khat(const float* kernel_host, const int kd[3]);
@@ -79,7 +82,8 @@ class Convolver {
 
   private:
     XArgs base_xargs(const TileGeom& t) const;
-    void col(int axis, int mode, const cpx* khat);
+    void col(int axis, int mode, const cpx* khat, int z0 = 0, int z1 = -1);
+    void xpass(int kind, XArgs a, int z0 = 0, int z1 = -1);
     Geometry g_;
     int xmode_;
     int T_[3];     // real tile extents
@@ -94,6 +98,7 @@ class Convolver {
     float* kpad_ = nullptr;
     // software L2 prefetch distance in CTAs for the x, y and z passes (MVD_PF_X / MVD_PF_Y / MVD_PF_Z override)
     int pf_x_ = 74, pf_y_ = 296, pf_z_ = 148;
+    int chunk_planes_ = 0;  // planes per L2-resident chunk of the x/y pass chains (0 = whole tile per launch)
     // profiling
     void mark(int pass);
     bool prof_on_ = false;

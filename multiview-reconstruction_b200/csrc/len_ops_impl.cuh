@@ -16,7 +16,7 @@ constexpr int min_blocks_for(size_t smem_bytes, int threads, int want) {
     return b < 1 ? 1 : b;
 }
 template <class P> constexpr int col_min_blocks() { return min_blocks_for(ColSmem<P>::bytes(), P::THREADS, 3); }
-template <class P> constexpr int x_min_blocks() { return min_blocks_for(XLay<P>::bytes(), P::XTHREADS, 4); }
+template <class P> constexpr int x_min_blocks() { return min_blocks_for(XLay<P>::bytes(), P::XTHREADS, (P::R1 > 20 || P::R2 > 20 || P::R3 > 20) ? 3 : 4); }
 
 #ifndef MVD_HOST_EMU
 template <class P, int MODE>
@@ -40,11 +40,14 @@ inline int carveout_pref() {   // MVD_CARVEOUT: -1 = driver default, 0..100 = pr
     return v;
 }
 
-template <class P>
+// P: plan of the column (y/z) kernels; PX: plan of the x kernels (same length, its own radices / threading).  The two may differ
+// because the scrambled frequency order of an axis only has to be consistent among the kernels that transform that axis.
+template <class P, class PX>
 struct LenImpl {
+    static_assert(P::N == PX::N, "column and x plans must describe the same length");
     static constexpr size_t smem_col = ColSmem<P>::bytes();
-    static constexpr size_t smem_x = XLay<P>::bytes();
-    static_assert(sizeof(cpx) * XLay<P>::TILE >= (sizeof(double) + sizeof(float)) * P::XTHREADS, "reduction scratch must fit in the tile");
+    static constexpr size_t smem_x = XLay<PX>::bytes();
+    static_assert(sizeof(cpx) * XLay<PX>::TILE >= (sizeof(double) + sizeof(float)) * PX::XTHREADS, "reduction scratch must fit in the tile");
 
     template <int MODE>
     static void col(const ColArgs& a, int gx, int gy, stream_t s) {
@@ -71,17 +74,17 @@ struct LenImpl {
         (void)s;
         std::vector<unsigned char> raw(smem_x + 16);
         cpx* sm = reinterpret_cast<cpx*>(raw.data());
-        LineInfo* li = reinterpret_cast<LineInfo*>(sm + XLay<P>::TILE + XLay<P>::NTAB);
-        HostExec ex(P::XTHREADS);
-        for (int bx = 0; bx < nblocks; ++bx) x_pass_body<P, KIND>(ex, a, bx, sm, li);
+        LineInfo* li = reinterpret_cast<LineInfo*>(sm + XLay<PX>::TILE + XLay<PX>::NTAB);
+        HostExec ex(PX::XTHREADS);
+        for (int bx = 0; bx < nblocks; ++bx) x_pass_body<PX, KIND>(ex, a, bx, sm, li);
 #else
         static bool attr_done = false;
         if (!attr_done) {
-            MVD_CUDA_CHECK(cudaFuncSetAttribute(x_kernel<P, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
-            if (carveout_pref() >= 0) MVD_CUDA_CHECK(cudaFuncSetAttribute(x_kernel<P, KIND>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pref()));
+            MVD_CUDA_CHECK(cudaFuncSetAttribute(x_kernel<PX, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+            if (carveout_pref() >= 0) MVD_CUDA_CHECK(cudaFuncSetAttribute(x_kernel<PX, KIND>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pref()));
             attr_done = true;
         }
-        x_kernel<P, KIND><<<nblocks, P::XTHREADS, smem_x, s>>>(a);
+        x_kernel<PX, KIND><<<nblocks, PX::XTHREADS, smem_x, s>>>(a);
         MVD_CUDA_CHECK(cudaGetLastError());
 #endif
     }
@@ -103,13 +106,13 @@ struct LenImpl {
         }
     }
     static const LenOps* ops() {
-        static const LenOps o = {P::N, P::R1, P::R2, P::R3, P::T, P::W, P::XT, P::XL, P::THREADS, P::XTHREADS, smem_col, smem_x,
-                                 XLay<P>::NTW, &fill_xtw<P>, &launch_col, &launch_x};
+        static const LenOps o = {P::N, P::R1, P::R2, P::R3, P::T, P::W, PX::XT, PX::XL, P::THREADS, PX::XTHREADS, smem_col, smem_x,
+                                 XLay<PX>::NTW, &fill_xtw<PX>, &launch_col, &launch_x};
         return &o;
     }
 };
 
 }  // namespace mvd
 
-#define MVD_DEFINE_LEN(N, R1, R2, R3, T, W, XT, XL) \
-    namespace mvd { const LenOps* len_ops_##N() { return LenImpl<Plan<N, R1, R2, R3, T, W, XT, XL>>::ops(); } }
+#define MVD_DEFINE_LEN(N, R1, R2, R3, T, W, XR1, XR2, XR3, XT, XL) \
+    namespace mvd { const LenOps* len_ops_##N() { return LenImpl<Plan<N, R1, R2, R3, T, W, 1, 1>, Plan<N, XR1, XR2, XR3, 1, 1, XT, XL>>::ops(); } }

@@ -23,6 +23,8 @@ BOX_BYTES = [8, 8, 12, 8, 12, 8, 12, 8, 16]
 
 
 def main():
+    if os.environ.get("MVD_LIB"):                 # development only: A/B a variant build of the library
+        m._LIB = m.Lib(os.environ["MVD_LIB"])
     name = sys.argv[1] if len(sys.argv) > 1 else "c3"
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     max_len = int(sys.argv[3]) if len(sys.argv) > 3 else 0
