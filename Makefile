@@ -21,11 +21,11 @@ HDRS      := $(CSRC)/fft_codelets.cuh $(CSRC)/fft_passes.cuh $(CSRC)/backend.h $
 
 LENS      := $(shell MVD_LENGTHS="$(MVD_LENGTHS)" python3 $(CSRC)/gen_lengths.py $(GEN))
 LENOBJ    := $(foreach n,$(LENS),$(BUILD)/obj/len_$(n).o)
-OBJ       := $(LENOBJ) $(BUILD)/obj/registry.o $(BUILD)/obj/engine.o $(BUILD)/obj/capi.o
+OBJ       := $(LENOBJ) $(BUILD)/obj/registry.o $(BUILD)/obj/engine.o $(BUILD)/obj/pointwise.o $(BUILD)/obj/capi.o
 
 HLENS     := $(shell MVD_LENGTHS="$(HOSTEMU_LENGTHS)" python3 $(CSRC)/gen_lengths.py $(GENH))
 HLENOBJ   := $(foreach n,$(HLENS),$(BUILD)/hostemu/obj/len_$(n).o)
-HOBJ      := $(HLENOBJ) $(BUILD)/hostemu/obj/registry.o $(BUILD)/hostemu/obj/engine.o $(BUILD)/hostemu/obj/capi.o
+HOBJ      := $(HLENOBJ) $(BUILD)/hostemu/obj/registry.o $(BUILD)/hostemu/obj/engine.o $(BUILD)/hostemu/obj/pointwise.o $(BUILD)/hostemu/obj/capi.o
 
 .PHONY: all hostemu clean fft_emu_test
 all: $(PKG)/libmvdecon.so
@@ -42,6 +42,9 @@ $(BUILD)/obj/registry.o: $(GEN)/registry.cpp $(HDRS)
 $(BUILD)/obj/engine.o: $(CSRC)/engine.cpp $(HDRS)
 	@mkdir -p $(BUILD)/obj
 	$(NVCC) $(NVFLAGS) -I$(CSRC) -x cu -c $< -o $@ 2> $(BUILD)/ptxas_engine.log || (cat $(BUILD)/ptxas_engine.log; false)
+$(BUILD)/obj/pointwise.o: $(CSRC)/pointwise.cpp $(HDRS)
+	@mkdir -p $(BUILD)/obj
+	$(NVCC) $(NVFLAGS) -I$(CSRC) -x cu -c $< -o $@ 2> $(BUILD)/ptxas_pointwise.log || (cat $(BUILD)/ptxas_pointwise.log; false)
 $(BUILD)/obj/capi.o: $(CSRC)/capi.cpp $(HDRS)
 	@mkdir -p $(BUILD)/obj
 	$(NVCC) $(NVFLAGS) -I$(CSRC) -x cu -c $< -o $@ 2> $(BUILD)/ptxas_capi.log || (cat $(BUILD)/ptxas_capi.log; false)
@@ -56,6 +59,9 @@ $(BUILD)/hostemu/obj/registry.o: $(GENH)/registry.cpp $(HDRS)
 	@mkdir -p $(BUILD)/hostemu/obj
 	$(CXX) $(HOSTFLAGS) -x c++ -c $< -o $@
 $(BUILD)/hostemu/obj/engine.o: $(CSRC)/engine.cpp $(HDRS)
+	@mkdir -p $(BUILD)/hostemu/obj
+	$(CXX) $(HOSTFLAGS) -x c++ -c $< -o $@
+$(BUILD)/hostemu/obj/pointwise.o: $(CSRC)/pointwise.cpp $(HDRS)
 	@mkdir -p $(BUILD)/hostemu/obj
 	$(CXX) $(HOSTFLAGS) -x c++ -c $< -o $@
 $(BUILD)/hostemu/obj/capi.o: $(CSRC)/capi.cpp $(HDRS)

@@ -110,6 +110,29 @@ MVD_API int mvd_set_psi(mvd_context* ctx, const float* psi_host);
 MVD_API int mvd_get_psi(mvd_context* ctx, float* psi_host);
 MVD_API int mvd_set_max_intensities(mvd_context* ctx, const float* max_per_view);
 
+/* PsiInit on the device (M/process/deconvolution/init/PsiInit.java:34 ordinals FUSED_BLURRED=0, AVG=1, APPROX_AVG=2; FROM_FILE / FROM_RAI
+ * are mvd_set_psi + mvd_set_max_intensities).  Sets psi and the per-view maxima from the views already handed over
+ * (PsiInitBlurredFused.java:63-127, PsiInitAvgPrecise.java:52-112, PsiInitAvgApprox.java:47-99).  sigma: Gaussian of FUSED_BLURRED
+ * (reference default 5.0).  avg_out: PsiInit.getAvg() (APPROX_AVG reports -1 like the reference); max_out: num_views values.
+ * Fails like the reference when no view covers the volume.  On a sharded context only FUSED_BLURRED is available (psi halos must be
+ * exchanged afterwards; the maxima are per shard and must be all-reduced by the host).                                               */
+enum { MVD_PSI_FUSED_BLURRED = 0, MVD_PSI_AVG = 1, MVD_PSI_APPROX_AVG = 2 };
+MVD_API int mvd_psi_init(mvd_context* ctx, int type, double sigma, double* avg_out, float* max_out);
+
+/* Weight masks on the device.  mvd_make_blending_weights: cosine blending of view v's axis-aligned box [box_min, box_max] (global
+ * integer coordinates, inclusive; BlendingRealRandomAccess.computeWeight, M/process/fusion/transformed/weights/BlendingRealRandomAccess.java:95-130)
+ * written into the context-owned weight volume of view v (mvd_set_view may be called with weight_host = NULL for such views).
+ * mvd_normalize_weights: NormalizingRandomAccess over all views in place (normalization/NormalizingRandomAccess.java:75-109,183-214);
+ * reference defaults: osem_speedup 1, additional_smooth 0, max_diff_range 0.1, scaling_range 0.05.  mvd_get_weight: download.        */
+MVD_API int mvd_make_blending_weights(mvd_context* ctx, int v, const int box_min[3], const int box_max[3], const float border[3], const float blending[3]);
+MVD_API int mvd_normalize_weights(mvd_context* ctx, double osem_speedup, int additional_smooth, float max_diff_range, float scaling_range);
+MVD_API int mvd_get_weight(mvd_context* ctx, int v, float* weight_host);
+
+/* MultiViewDeconvolutionMul.runNextIteration (M/process/deconvolution/MultiViewDeconvolutionMul.java:116-245,
+ * iteration/mul/ComputeBlockMulThreadCPU.java:87-188, mul/DeconvolutionMethods.java:370-419): ONE psi update per iteration from all
+ * views (geometric mean of the per-view integrals, summed weights capped at 1, max := mean of the per-view maxima).                 */
+MVD_API int mvd_run_iteration_mul(mvd_context* ctx, double stats[2]);
+
 /* One view update of MultiViewDeconvolutionSeq.runNextIteration (:69-176): psi <- update(psi, view v).
  * stats (may be NULL) receives {sumChange, maxChange} over the owned voxels (IterationStatistics, ComputeBlockThread.java:64-68). */
 MVD_API int mvd_run_view_update(mvd_context* ctx, int v, double stats[2]);

@@ -82,6 +82,11 @@ SYMBOLS = {
     "mvd_set_psi": (C.c_int, [C.c_void_p, _F]),
     "mvd_get_psi": (C.c_int, [C.c_void_p, _F]),
     "mvd_set_max_intensities": (C.c_int, [C.c_void_p, _F]),
+    "mvd_psi_init": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _D, _F]),
+    "mvd_make_blending_weights": (C.c_int, [C.c_void_p, C.c_int, _I, _I, _F, _F]),
+    "mvd_normalize_weights": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_float, C.c_float]),
+    "mvd_get_weight": (C.c_int, [C.c_void_p, C.c_int, _F]),
+    "mvd_run_iteration_mul": (C.c_int, [C.c_void_p, _D]),
     "mvd_run_view_update": (C.c_int, [C.c_void_p, C.c_int, _D]),
     "mvd_run_iterations": (C.c_int, [C.c_void_p, C.c_int, _D]),
     "mvd_enqueue_view_update": (C.c_int, [C.c_void_p, C.c_int]),
@@ -245,8 +250,8 @@ class DeconView:
     def __init__(self, image: np.ndarray, weight: np.ndarray, kernel: np.ndarray, psfType: PSFTYPE = PSFTYPE.INDEPENDENT,
                  title: Optional[str] = None):
         self.image = image if isinstance(image, DeviceArray) else _f32(image)
-        self.weight = weight if isinstance(weight, DeviceArray) else _f32(weight)
-        if self.image.shape != self.weight.shape or self.image.ndim != 3:
+        self.weight = weight if (weight is None or isinstance(weight, DeviceArray)) else _f32(weight)   # None: generated on the device
+        if (self.weight is not None and self.image.shape != self.weight.shape) or self.image.ndim != 3:
             raise MvdError("image and weight must be 3-d volumes of identical size")
         self.psf = DeconViewPSF(kernel, psfType)
         self.title = title
@@ -301,6 +306,8 @@ class DeconViews:
                     if not (isinstance(v.image, DeviceArray) and isinstance(v.weight, DeviceArray)):
                         raise MvdError("image and weight of a view must both be host arrays or both DeviceArrays")
                     self.lib.check(self.lib.dll.mvd_set_view_device(self._ctx, i, C.c_void_p(v.image.ptr), C.c_void_p(v.weight.ptr)))
+                elif v.weight is None:
+                    self.lib.check(self.lib.dll.mvd_set_view(self._ctx, i, _fp(v.image), None))
                 else:
                     self.lib.check(self.lib.dll.mvd_set_view(self._ctx, i, _fp(v.image), _fp(v.weight)))
                 self.lib.check(self.lib.dll.mvd_set_psf(self._ctx, i, _fp(v.psf.psf), _i3(_xyz(v.psf.psf))))
@@ -343,6 +350,21 @@ class DeconViews:
         n = (C.c_longlong * 9)()
         self.lib.check(self.lib.dll.mvd_get_pass_times(self._ctx, ms, n, 1 if reset else 0))
         return [float(x) for x in ms], [int(x) for x in n]
+
+    # ---- weight masks on the device (BlendingRealRandomAccess + NormalizingRandomAccess) --------------------------------
+    def makeBlendingWeights(self, v: int, box_min_xyz, box_max_xyz, border=(0.0, 0.0, 0.0), blending=(12.0, 12.0, 12.0)):
+        b = (C.c_float * 3)(*[float(x) for x in border])
+        r = (C.c_float * 3)(*[float(x) for x in blending])
+        self.lib.check(self.lib.dll.mvd_make_blending_weights(self._ctx, int(v), _i3(box_min_xyz), _i3(box_max_xyz), b, r))
+
+    def normalizeWeights(self, osemspeedup: float = 1.0, additionalSmoothBlending: bool = False, maxDiffRange: float = 0.1, scalingRange: float = 0.05):
+        self.lib.check(self.lib.dll.mvd_normalize_weights(self._ctx, float(osemspeedup), 1 if additionalSmoothBlending else 0,
+                                                           C.c_float(maxDiffRange), C.c_float(scalingRange)))
+
+    def getWeight(self, v: int) -> np.ndarray:
+        w = np.empty(self.local_shape, dtype=np.float32)
+        self.lib.check(self.lib.dll.mvd_get_weight(self._ctx, int(v), _fp(w)))
+        return w
 
     def psi_device_ptr(self) -> int:
         p = C.c_void_p()
@@ -389,6 +411,45 @@ class PsiInitFromRAI:
         return self.max
 
 
+class _PsiInitDevice:
+    """PsiInit variants that run on the device from the views held by the context."""
+    TYPE = -1
+
+    def __init__(self, sigma: float = 5.0):
+        self.sigma = float(sigma)
+        self.avg = -1.0
+        self.max = None
+
+    def runInitialization(self, views: "DeconViews") -> bool:
+        avg = C.c_double()
+        mx = (C.c_float * len(views.getViews()))()
+        views.lib.check(views.lib.dll.mvd_psi_init(views._ctx, self.TYPE, self.sigma, C.byref(avg), mx))
+        self.avg = float(avg.value)
+        self.max = np.array(list(mx), dtype=np.float32)
+        return True
+
+    def getAvg(self) -> float:
+        return self.avg
+
+    def getMax(self):
+        return self.max
+
+
+class PsiInitBlurredFused(_PsiInitDevice):
+    """M/process/deconvolution/init/PsiInitBlurredFused.java:63-127 (default PsiInit; sigma = 5)."""
+    TYPE = 0
+
+
+class PsiInitAvgPrecise(_PsiInitDevice):
+    """M/process/deconvolution/init/PsiInitAvgPrecise.java:52-112."""
+    TYPE = 1
+
+
+class PsiInitAvgApprox(_PsiInitDevice):
+    """M/process/deconvolution/init/PsiInitAvgApprox.java:47-99 (getAvg() returns -1 like the reference)."""
+    TYPE = 2
+
+
 class MultiViewDeconvolutionSeq:
     """MultiViewDeconvolution + MultiViewDeconvolutionSeq (M/process/deconvolution/MultiViewDeconvolution.java:90-200,
     MultiViewDeconvolutionSeq.java:58-180): OSEM loop, psi updated after every view, resident on the device."""
@@ -398,13 +459,17 @@ class MultiViewDeconvolutionSeq:
         self.numIterations = int(numIterations)
         self.it = 0
         self.lib = views.lib
-        self.max = np.asarray(psiInit.getMax(), dtype=np.float32)
-        if self.max.shape != (len(views.getViews()),):
-            raise MvdError("need one max intensity per view")
-        if psiInit.psi0.shape != views.local_shape:
-            raise MvdError("psi dimensions must equal the view dimensions")
-        self.lib.check(self.lib.dll.mvd_set_max_intensities(views._ctx, _fp(self.max)))
-        self.lib.check(self.lib.dll.mvd_set_psi(views._ctx, _fp(psiInit.psi0)))
+        if isinstance(psiInit, _PsiInitDevice):              # psiInit.runInitialization( psi, views, service ), MultiViewDeconvolution.java:115-135
+            psiInit.runInitialization(views)
+            self.max = np.asarray(psiInit.getMax(), dtype=np.float32)
+        else:
+            self.max = np.asarray(psiInit.getMax(), dtype=np.float32)
+            if self.max.shape != (len(views.getViews()),):
+                raise MvdError("need one max intensity per view")
+            if psiInit.psi0.shape != views.local_shape:
+                raise MvdError("psi dimensions must equal the view dimensions")
+            self.lib.check(self.lib.dll.mvd_set_max_intensities(views._ctx, _fp(self.max)))
+            self.lib.check(self.lib.dll.mvd_set_psi(views._ctx, _fp(psiInit.psi0)))
         self.stats: List[List[IterationStatistics]] = []
 
     def initWasSuccessful(self) -> bool:
@@ -435,6 +500,23 @@ class MultiViewDeconvolutionSeq:
         psi = np.empty(self.views.local_shape, dtype=np.float32)
         self.lib.check(self.lib.dll.mvd_get_psi(self.views._ctx, _fp(psi)))
         return psi
+
+
+class MultiViewDeconvolutionMul(MultiViewDeconvolutionSeq):
+    """MultiViewDeconvolutionMul (M/process/deconvolution/MultiViewDeconvolutionMul.java:116-245): one psi update per iteration from
+    all views (geometric mean of the integrals)."""
+
+    def runNextIteration(self) -> List[IterationStatistics]:
+        self.it += 1
+        st = (C.c_double * 2)()
+        self.lib.check(self.lib.dll.mvd_run_iteration_mul(self.views._ctx, st))
+        out = [IterationStatistics(float(st[0]), float(st[1]))]
+        self.stats.append(out)
+        return out
+
+    def runIterations(self) -> None:
+        while self.it < self.numIterations:
+            self.runNextIteration()
 
 
 class ComputeBlockSeqThreadB200:

@@ -87,7 +87,7 @@ int mvd_destroy(mvd_context* ctx) {
 }
 
 int mvd_set_view(mvd_context* ctx, int v, const float* img, const float* weight) {
-    return guarded([&] { require(ctx && img && weight, "null argument"); ctx->engine->set_view_host(v, img, weight); });
+    return guarded([&] { require(ctx && img, "null argument"); ctx->engine->set_view_host(v, img, weight); });
 }
 int mvd_set_view_device(mvd_context* ctx, int v, const float* img, const float* weight) {
     return guarded([&] { require(ctx && img && weight, "null argument"); ctx->engine->set_view_device(v, img, weight); });
@@ -123,6 +123,31 @@ int mvd_get_psi(mvd_context* ctx, float* psi) {
 }
 int mvd_set_max_intensities(mvd_context* ctx, const float* mx) {
     return guarded([&] { require(ctx && mx, "null argument"); ctx->engine->set_max_intensity(mx); });
+}
+int mvd_psi_init(mvd_context* ctx, int type, double sigma, double* avg_out, float* max_out) {
+    return guarded([&] { require(ctx, "null context"); ctx->engine->psi_init(type, sigma, avg_out, max_out); });
+}
+int mvd_make_blending_weights(mvd_context* ctx, int v, const int box_min[3], const int box_max[3], const float border[3], const float blending[3]) {
+    return guarded([&] {
+        require(ctx && box_min && box_max && border && blending, "null argument");
+        for (int d = 0; d < 3; ++d) require(blending[d] > 0.f, "blending range must be positive");
+        ctx->engine->make_blending_weights(v, box_min, box_max, border, blending);
+    });
+}
+int mvd_normalize_weights(mvd_context* ctx, double osem_speedup, int additional_smooth, float max_diff_range, float scaling_range) {
+    return guarded([&] { require(ctx, "null context"); ctx->engine->normalize_view_weights(osem_speedup, additional_smooth != 0, max_diff_range, scaling_range); });
+}
+int mvd_get_weight(mvd_context* ctx, int v, float* out) {
+    return guarded([&] { require(ctx && out, "null argument"); ctx->engine->get_weight_host(v, out); });
+}
+int mvd_run_iteration_mul(mvd_context* ctx, double stats[2]) {
+    return guarded([&] {
+        require(ctx, "null context");
+        ctx->engine->iteration_mul();
+        IterStats s{0, -1};
+        ctx->engine->fetch_stats(1, &s);
+        if (stats) { stats[0] = s.sum_change; stats[1] = s.max_change; }
+    });
 }
 int mvd_run_view_update(mvd_context* ctx, int v, double stats[2]) {
     return guarded([&] {

@@ -332,6 +332,21 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
     }
 }
 
+void Convolver::integral(const float* psi_in, const float* img, const cpx* k1hat, const cpx* k2hat, float* integral_out) {
+    for (const TileGeom& t : tiles_) {
+        XArgs a = base_xargs(t);
+        a.src = psi_in;
+        a.ext = EXT_MIRROR;
+        xpass(X_FWD, a);
+        col(1, COL_FWD, nullptr); col(2, COL_CONV, k1hat); col(1, COL_INV, nullptr);
+        a.src = img;
+        xpass(X_RATIO, a);
+        col(1, COL_FWD, nullptr); col(2, COL_CONV, k2hat); col(1, COL_INV, nullptr);
+        a.dst = integral_out;
+        xpass(X_INV, a);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel helpers (host; kernels are a few thousand voxels)
 // ------------------------------------------------------------------------------------------------
@@ -407,6 +422,8 @@ Engine::~Engine() {
     }
     dev::free_(psi_[0]); dev::free_(psi_[1]);
     dev::free_(part_sum_); dev::free_(part_max_); dev::free_(stats_dev_);
+    for (float* p : integral_) dev::free_(p);
+    dev::free_(lut_dev_); dev::free_(acc_dev_); dev::free_(max_dev_);
     conv_.reset();
     tables_.reset();
     dev::stream_destroy(stream_);
@@ -420,7 +437,8 @@ void Engine::set_view_host(int v, const float* img, const float* weight) {
     if (!vw.img_owned) vw.img_owned = (float*)dev::alloc(bytes);
     if (!vw.weight_owned) vw.weight_owned = (float*)dev::alloc(bytes);
     dev::h2d(vw.img_owned, img, bytes, stream_);
-    dev::h2d(vw.weight_owned, weight, bytes, stream_);
+    if (weight) dev::h2d(vw.weight_owned, weight, bytes, stream_);       // weight == nullptr: generated on the device later
+    else dev::zero(vw.weight_owned, bytes, stream_);
     vw.img = vw.img_owned;
     vw.weight = vw.weight_owned;
 }
@@ -558,12 +576,7 @@ void Engine::get_psi_host(float* psi) {
 
 int Engine::launches_per_view_update() const { return conv_ ? conv_->launches_per_update() + 2 : 0; }
 
-void Engine::view_update(int v) {
-    if (!inited_) throw Error("init_views() has not been called");
-    if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
-    dev::set_device(cfg_.device);
-    View& vw = views_[v];
-    if (!vw.img || !vw.weight) throw Error("view without image/weight");
+void Engine::ensure_stats_slot() {
     if (stats_count_ >= stats_cap_) {
         // grow the statistics ring (keeps earlier entries)
         const int ncap = stats_cap_ ? stats_cap_ * 2 : 1024;
@@ -572,6 +585,167 @@ void Engine::view_update(int v) {
         stats_dev_ = n;
         stats_cap_ = ncap;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PsiInit on the device (M/process/deconvolution/init/PsiInitBlurredFused.java:63-127, PsiInitAvgPrecise.java:52-112,
+// PsiInitAvgApprox.java:47-99)
+// ------------------------------------------------------------------------------------------------
+void Engine::psi_init(int type, double sigma, double* avg_out, float* max_out) {
+    dev::set_device(cfg_.device);
+    const int V = cfg_.num_views;
+    if (V > MVD_MAX_VIEWS) throw Error("too many views for the device PsiInit");
+    const Geometry& g = cfg_.geom;
+    const bool sharded = g.own_lo[2] != 0 || g.own_hi[2] != g.gdim[2];
+    const long long plane = (long long)g.vol[0] * g.vol[1], n = (long long)local_voxels();
+    const long long own0 = (long long)(g.own_lo[2] - g.goff[2]) * plane, own1 = (long long)(g.own_hi[2] - g.goff[2]) * plane;
+    ViewPtrs vp;
+    for (int j = 0; j < V; ++j) {
+        if (!views_[j].img) throw Error("view without image");
+        vp.img[j] = views_[j].img;
+        vp.weight[j] = views_[j].weight;
+    }
+    if (!acc_dev_) acc_dev_ = (double*)dev::alloc(sizeof(double) * 2);
+    if (!max_dev_) max_dev_ = (float*)dev::alloc(sizeof(float) * MVD_MAX_VIEWS);
+    double acc[2] = {0, 0};
+    float mx[MVD_MAX_VIEWS] = {0};
+    double avg = 0, avg_reported = 0;
+    if (type == PSI_FUSED_BLURRED || type == PSI_AVG) {
+        if (type == PSI_FUSED_BLURRED)
+            for (int j = 0; j < V; ++j) if (!views_[j].weight) throw Error("FUSED_BLURRED needs the view weights");
+        psi_fused_stats(stream_, vp, V, type == PSI_FUSED_BLURRED ? psi_[cur_] : nullptr, n, own0, own1, acc_dev_, max_dev_);
+        dev::d2h(acc, acc_dev_, sizeof(acc), stream_);
+        dev::d2h(mx, max_dev_, sizeof(float) * V, stream_);
+        dev::sync(stream_);
+        if (acc[1] == 0) throw Error("None of the views covers the deconvolved area, did you set the bounding box right?");   // PsiInitBlurredFused.java:95-99
+        avg = acc[0] / acc[1];
+        if (avg != avg) avg = 1.0;
+        avg_reported = avg;
+        if (type == PSI_AVG) {
+            if (sharded) throw Error("PsiInit AVG on a sharded context needs the global average: initialise psi from the host");
+            fill_volume(stream_, psi_[cur_], n, (float)avg);
+        } else {
+            // Gauss3.gauss(sigma, extendMirrorSingle(psi), psi) -- separable Gaussian expressed as one 3-d kernel through the FFT passes
+            const std::vector<double> half = gauss3_halfkernel(sigma);
+            const int r = (int)half.size() - 1, k = 2 * r + 1;
+            std::vector<float> k3((size_t)k * k * k);
+            for (int z = 0; z < k; ++z)
+                for (int y = 0; y < k; ++y)
+                    for (int x = 0; x < k; ++x)
+                        k3[((size_t)z * k + y) * k + x] = (float)(half[std::abs(z - r)] * half[std::abs(y - r)] * half[std::abs(x - r)]);
+            Reach r1[3], r2[3];
+            const int kd[3] = {k, k, k};
+            for (int d = 0; d < 3; ++d) { r1[d] = reach_of(k); r2[d] = Reach{0, 0}; }
+            if (sharded && ((g.own_lo[2] != 0 && g.own_lo[2] - r < g.goff[2]) || (g.own_hi[2] != g.gdim[2] && g.own_hi[2] + r > g.goff[2] + g.vol[2])))
+                throw Error("sharded FUSED_BLURRED: the local arrays need at least (int)(3*sigma+0.5)+1 halo planes");
+            Convolver cv(g, r1, r2, 0, cfg_.max_len, stream_, tables_.get());
+            cpx* khat = cv.build_khat(k3.data(), kd);
+            dev::d2d(psi_[cur_ ^ 1], psi_[cur_], sizeof(float) * n, stream_);     // halo planes keep the un-blurred values until the exchange
+            cv.conv(psi_[cur_], psi_[cur_ ^ 1], khat, EXT_MIRROR, 0.f);
+            dev::sync(stream_);
+            dev::free_(khat);
+            cur_ ^= 1;
+        }
+    } else if (type == PSI_APPROX_AVG) {
+        if (sharded) throw Error("PsiInit APPROX_AVG is not available on a sharded context");
+        for (int j = 0; j < V; ++j) {
+            dev::zero(acc_dev_, sizeof(double) * 2, stream_);
+            const float lowest = -3.0e38f;
+            dev::h2d(max_dev_, &lowest, sizeof(float), stream_);
+            dev::sync(stream_);
+            slice_stats(stream_, views_[j].img, g.vol[0], (long long)g.vol[1] * g.vol[2], acc_dev_, max_dev_);
+            dev::d2h(acc, acc_dev_, sizeof(acc), stream_);
+            dev::d2h(&mx[j], max_dev_, sizeof(float), stream_);
+            dev::sync(stream_);
+            avg += acc[0] / acc[1];                          // the slice is visited numDimensions times: same mean
+        }
+        avg /= (double)V;
+        if (avg != avg) avg = 1.0;
+        avg_reported = -1.0;                                 // PsiInitAvgApprox.getAvg(): the field is shadowed by a local (:40,57,80)
+        fill_volume(stream_, psi_[cur_], n, (float)avg);
+    } else {
+        throw Error("unknown PsiInit type");
+    }
+    for (int j = 0; j < V; ++j) views_[j].max_intensity = mx[j];
+    dev::sync(stream_);
+    if (avg_out) *avg_out = avg_reported;
+    if (max_out) for (int j = 0; j < V; ++j) max_out[j] = mx[j];
+}
+
+void Engine::make_blending_weights(int v, const int box_min[3], const int box_max[3], const float border[3], const float blending[3]) {
+    if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
+    dev::set_device(cfg_.device);
+    View& vw = views_[v];
+    if (vw.weight && !vw.weight_owned) throw Error("the weight of this view is borrowed device memory; cannot generate into it");
+    if (!vw.weight_owned) vw.weight_owned = (float*)dev::alloc(sizeof(float) * local_voxels());
+    vw.weight = vw.weight_owned;
+    if (!lut_dev_) {
+        const std::vector<double> lut = blend_lut();
+        lut_dev_ = (double*)dev::alloc(sizeof(double) * lut.size());
+        dev::h2d(lut_dev_, lut.data(), sizeof(double) * lut.size(), stream_);
+        dev::sync(stream_);
+    }
+    blend_weights(stream_, vw.weight_owned, lut_dev_, cfg_.geom.vol, cfg_.geom.goff, box_min, box_max, border, blending);
+}
+
+void Engine::normalize_view_weights(double osem_speedup, bool additional_smooth, float max_diff_range, float scaling_range) {
+    dev::set_device(cfg_.device);
+    const int V = cfg_.num_views;
+    if (V > MVD_MAX_VIEWS) throw Error("too many views");
+    WeightPtrs w;
+    for (int j = 0; j < V; ++j) {
+        if (!views_[j].weight_owned || views_[j].weight != views_[j].weight_owned) throw Error("normalisation needs context-owned weights for every view");
+        w.w[j] = views_[j].weight_owned;
+    }
+    normalize_weights(stream_, w, V, (long long)local_voxels(), osem_speedup, additional_smooth, max_diff_range, scaling_range);
+}
+
+void Engine::get_weight_host(int v, float* out) {
+    if (v < 0 || v >= cfg_.num_views || !views_[v].weight) throw Error("no such weight");
+    dev::set_device(cfg_.device);
+    dev::d2h(out, views_[v].weight, sizeof(float) * local_voxels(), stream_);
+    dev::sync(stream_);
+}
+
+// MultiViewDeconvolutionMul.runNextIteration / ComputeBlockMulThreadCPU.runIteration (mul/ComputeBlockMulThreadCPU.java:87-188)
+void Engine::iteration_mul() {
+    if (!inited_) throw Error("init_views() has not been called");
+    dev::set_device(cfg_.device);
+    const int V = cfg_.num_views;
+    if (V > MVD_MAX_VIEWS) throw Error("too many views");
+    const Geometry& g = cfg_.geom;
+    const long long plane = (long long)g.vol[0] * g.vol[1], n = (long long)local_voxels();
+    const long long own0 = (long long)(g.own_lo[2] - g.goff[2]) * plane, own1 = (long long)(g.own_hi[2] - g.goff[2]) * plane;
+    if ((int)integral_.size() < V) {
+        integral_.resize(V, nullptr);
+        for (float*& p : integral_) if (!p) p = (float*)dev::alloc(sizeof(float) * n);
+    }
+    if (!max_dev_) max_dev_ = (float*)dev::alloc(sizeof(float) * MVD_MAX_VIEWS);
+    ensure_stats_slot();
+    MulPtrs mp;
+    double miv = 0;
+    for (int v = 0; v < V; ++v) {                            // all views from the SAME psi
+        View& vw = views_[v];
+        if (!vw.img || !vw.weight) throw Error("view without image/weight");
+        conv_->integral(psi_[cur_], vw.img, vw.k1hat, vw.k2hat, integral_[v]);
+        mp.integral[v] = integral_[v];
+        mp.weight[v] = vw.weight;
+        miv += (double)vw.max_intensity;
+    }
+    miv /= (double)V;                                        // :144-149
+    mul_combine(stream_, mp, V, psi_[cur_], psi_[cur_ ^ 1], n, own0, own1, cfg_.lambda, cfg_.min_value, (float)miv,
+                stats_dev_ + 2 * (size_t)stats_count_, max_dev_);
+    ++stats_count_;
+    cur_ ^= 1;
+}
+
+void Engine::view_update(int v) {
+    if (!inited_) throw Error("init_views() has not been called");
+    if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
+    dev::set_device(cfg_.device);
+    View& vw = views_[v];
+    if (!vw.img || !vw.weight) throw Error("view without image/weight");
+    ensure_stats_slot();
     const int nparts = conv_->num_tiles() * conv_->parts_per_tile();
     conv_->view_update(psi_[cur_], psi_[cur_ ^ 1], vw.img, vw.weight, vw.k1hat, vw.k2hat, cfg_.lambda, cfg_.min_value,
                        vw.max_intensity, part_sum_, part_max_);

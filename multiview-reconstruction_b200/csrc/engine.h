@@ -76,6 +76,8 @@ class Convolver {
     // one fused view update (P1..P9) over all tiles; partial stats -> part_sum/part_max [num_tiles*parts_per_tile]
     void view_update(const float* psi_in, float* psi_out, const float* img, const float* weight, const cpx* k1hat,
                      const cpx* k2hat, float lambda, float min_value, float max_intensity, double* part_sum, float* part_max);
+    // conv1 -> quotient -> conv2 without the update: the "integral" of one view (P1..P8 + real store), used by the Mul iteration
+    void integral(const float* psi_in, const float* img, const cpx* k1hat, const cpx* k2hat, float* integral_out);
     // per-pass CUDA-event timing (bench.py's roofline leg): P1..P9 -> slots 0..8
     void set_profiling(bool on) { prof_on_ = on; }
     void collect_pass_times(double ms[9], long long counts[9], bool reset);
@@ -118,6 +120,23 @@ void convolve_host(int device, stream_t s, Tables* tables, int max_len, const fl
 
 struct IterStats { double sum_change; double max_change; };
 
+// ---- point-wise device stages (pointwise.cpp) -------------------------------------------------------------------------
+#define MVD_MAX_VIEWS 16
+struct ViewPtrs { const float* img[MVD_MAX_VIEWS]; const float* weight[MVD_MAX_VIEWS]; };
+struct WeightPtrs { float* w[MVD_MAX_VIEWS]; };
+struct MulPtrs { const float* integral[MVD_MAX_VIEWS]; const float* weight[MVD_MAX_VIEWS]; };
+void psi_fused_stats(stream_t s, const ViewPtrs& vp, int V, float* psi, long long n, long long own0, long long own1, double* acc_dev, float* max_dev);
+void fill_volume(stream_t s, float* p, long long n, float v);
+void slice_stats(stream_t s, const float* img, int nx, long long nyz, double* acc_dev, float* max_dev);
+void blend_weights(stream_t s, float* out, const double* lut_dev, const int vol[3], const int goff[3], const int box_min[3], const int box_max[3],
+                   const float border[3], const float blending[3]);
+std::vector<double> blend_lut();
+void normalize_weights(stream_t s, const WeightPtrs& w, int V, long long n, double osem, bool smooth, float max_diff_range, float scaling_range);
+void mul_combine(stream_t st, const MulPtrs& p, int V, const float* psi_in, float* psi_out, long long n, long long own0, long long own1, float lambda,
+                 float min_value, float max_intensity, double* stats_dev, float* scratch_max_dev);
+std::vector<double> gauss3_halfkernel(double sigma);
+enum PsiInitType : int { PSI_FUSED_BLURRED = 0, PSI_AVG = 1, PSI_APPROX_AVG = 2 };
+
 class Engine {
   public:
     struct Config {
@@ -152,6 +171,14 @@ class Engine {
     void set_max_intensity(const float* mx) { for (int v = 0; v < cfg_.num_views; ++v) views_[v].max_intensity = mx[v]; }
     float max_intensity(int v) const { return views_[v].max_intensity; }
 
+    // PsiInit on the device (PsiInitBlurredFused / PsiInitAvgPrecise / PsiInitAvgApprox): sets psi and the per-view maxima
+    void psi_init(int type, double sigma, double* avg_out, float* max_out);
+    // weight masks on the device: cosine blending of a view's box, then NormalizingRandomAccess over all views
+    void make_blending_weights(int v, const int box_min[3], const int box_max[3], const float border[3], const float blending[3]);
+    void normalize_view_weights(double osem_speedup, bool additional_smooth, float max_diff_range, float scaling_range);
+    void get_weight_host(int v, float* out);
+    // MultiViewDeconvolutionMul.runNextIteration: one psi update from all views (geometric mean of the integrals)
+    void iteration_mul();
     void view_update(int v);                               // asynchronous on the engine stream
     void fetch_stats(int count, IterStats* out);           // last `count` view updates (synchronises)
     void run_iterations(int n, IterStats* out /* n*V or null */);
@@ -192,6 +219,11 @@ class Engine {
     double* part_sum_ = nullptr;
     float* part_max_ = nullptr;
     double* stats_dev_ = nullptr;   // ring of {sum,max} pairs
+    void ensure_stats_slot();
+    std::vector<float*> integral_;  // Mul iteration: one integral volume per view
+    double* lut_dev_ = nullptr;     // cosine blending LUT
+    double* acc_dev_ = nullptr;     // {sum, count} scratch
+    float* max_dev_ = nullptr;      // per-view maxima scratch
     int stats_cap_ = 0, stats_count_ = 0;
 };
 

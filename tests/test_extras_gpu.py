@@ -1,0 +1,24 @@
+"""PsiInit / weight masks / Mul iteration on the GPU through the C ABI vs the oracle."""
+import pytest
+
+import extras_checks as X
+
+pytestmark = pytest.mark.gpu
+
+
+def test_weights_on_device_match_oracle(product_lib, oracle, small_dataset):
+    X.check_weights_on_device_match_oracle(product_lib, oracle, small_dataset)
+
+
+@pytest.mark.parametrize("smooth,osem", [(True, 1.0), (False, 2.5)])
+def test_weight_normalisation_variants(product_lib, oracle, small_dataset, smooth, osem):
+    X.check_weight_normalisation_variants(product_lib, oracle, small_dataset, smooth, osem)
+
+
+def test_psi_init_variants(product_lib, oracle, small_dataset):
+    X.check_psi_init_variants(product_lib, oracle, small_dataset)
+
+
+@pytest.mark.parametrize("lam", [0.0, 0.006])
+def test_mul_iteration_matches_oracle(product_lib, oracle, small_dataset, lam):
+    X.check_mul_iteration_matches_oracle(product_lib, oracle, small_dataset, lam)
