@@ -82,8 +82,8 @@ def synth_psf(view, num_views, size_xyz, sigma_xyz):
     return (g / g.sum()).astype(np.float32)
 
 
-def truth_slab(dims_zyx, z0, z1, seed):
-    """background 100 + point beads (count N/8192, amplitude U[500,4000]) restricted to planes [z0, z1)."""
+def truth_box(dims_zyx, y0, y1, z0, z1, seed):
+    """background 100 + point beads (count N/8192, amplitude U[500,4000]) restricted to rows [y0, y1) x planes [z0, z1)."""
     nz, ny, nx = dims_zyx
     nb = max(1, nz * ny * nx // 8192)
     idx = np.arange(nb, dtype=np.uint64)
@@ -91,9 +91,9 @@ def truth_slab(dims_zyx, z0, z1, seed):
     py = np.minimum((rng_uniform(seed, 2, idx) * ny).astype(np.int64), ny - 1)
     pz = np.minimum((rng_uniform(seed, 3, idx) * nz).astype(np.int64), nz - 1)
     amp = (500.0 + 3500.0 * rng_uniform(seed, 4, idx)).astype(np.float32)
-    out = np.full((z1 - z0, ny, nx), 100.0, dtype=np.float32)
-    keep = (pz >= z0) & (pz < z1)
-    np.add.at(out, (pz[keep] - z0, py[keep], px[keep]), amp[keep])
+    out = np.full((z1 - z0, y1 - y0, nx), 100.0, dtype=np.float32)
+    keep = (pz >= z0) & (pz < z1) & (py >= y0) & (py < y1)
+    np.add.at(out, (pz[keep] - z0, py[keep] - y0, px[keep]), amp[keep])
     return out
 
 
@@ -120,28 +120,30 @@ def blend_1d(n, lo, hi, rng=12.0, border=0.0, offset=0):
     return w.astype(np.float32)
 
 
-def make_slab_inputs(torch, lib, name, z0, z1, device):
-    """views (image, weight) on planes [z0, z1) of the global volume as torch device tensors + psi0 + per-view max."""
+def make_box_inputs(torch, lib, name, y0, y1, z0, z1, device):
+    """views (image, weight) on rows [y0, y1) x planes [z0, z1) of the global volume as torch device tensors + psi0 + per-view max."""
     dims, V, psf_xyz, sigma, lam, ptype = WORKLOADS[name]
     nz, ny, nx = dims
-    kz = psf_xyz[2]
-    m0, m1 = max(0, z0 - kz), min(nz, z1 + kz)            # margin so the slab edges see true neighbours
-    truth = truth_slab(dims, m0, m1, SEED)
+    ky, kz = psf_xyz[1], psf_xyz[2]
+    m0, m1 = max(0, z0 - kz), min(nz, z1 + kz)            # margins so the box edges see true neighbours
+    n0, n1 = max(0, y0 - ky), min(ny, y1 + ky)
+    truth = truth_box(dims, n0, n1, m0, m1, SEED)
     psfs = [synth_psf(v, V, psf_xyz, sigma) for v in range(V)]
     imgs, raws = [], []
     for v in range(V):
-        blurred = lib.convolve(truth, psfs[v], "mirror", device=device)[z0 - m0:z1 - m0]
+        blurred = np.ascontiguousarray(lib.convolve(truth, psfs[v], "mirror", device=device)[z0 - m0:z1 - m0, y0 - n0:y1 - n0])
         mn, mx = coverage_box(dims, v)
         t = torch.from_numpy(blurred).to(f"cuda:{device}")
         t.clamp_(min=1.0)                                     # minValueImg
-        mask = torch.zeros((z1 - z0, ny, nx), dtype=torch.bool, device=t.device)
+        mask = torch.zeros((z1 - z0, y1 - y0, nx), dtype=torch.bool, device=t.device)
         zs, ze = max(mn[2], z0) - z0, min(mx[2] + 1, z1) - z0
-        if ze > zs:
-            mask[zs:ze, mn[1]:mx[1] + 1, mn[0]:mx[0] + 1] = True
+        ys, ye = max(mn[1], y0) - y0, min(mx[1] + 1, y1) - y0
+        if ze > zs and ye > ys:
+            mask[zs:ze, ys:ye, mn[0]:mx[0] + 1] = True
         t.mul_(mask)                                          # outsideValueImg = 0
         imgs.append(t)
         wx = torch.from_numpy(blend_1d(nx, mn[0], mx[0])).to(t.device)
-        wy = torch.from_numpy(blend_1d(ny, mn[1], mx[1])).to(t.device)
+        wy = torch.from_numpy(blend_1d(y1 - y0, mn[1], mx[1], offset=y0)).to(t.device)
         wz = torch.from_numpy(blend_1d(z1 - z0, mn[2], mx[2], offset=z0)).to(t.device)
         raws.append((wz[:, None, None] * wy[None, :, None] * wx[None, None, :]).clamp_(max=1.0))
         del mask
@@ -286,21 +288,27 @@ def run_ours(args):
     name = args.config
     dims, V, psf_xyz, sigma, lam, ptype = WORKLOADS[name]
     nz, ny, nx = dims
-    H = psf_xyz[2] - 1                                       # psi halo planes per interior side (k1z/2 + k2z/2)
     from mvrecon_b200 import sharding
-    lo, hi = sharding.slab_range(nz, world, rank)
-    z0, z1 = sharding.extended_range(lo, hi, nz, H)
+    Hy, Hz = psf_xyz[1] - 1, psf_xyz[2] - 1                  # psi halo per interior side = k1/2 + k2/2 along that axis
+    py, pz = sharding.grid_for(world, ny, nz, (psf_xyz[1] - 1) // 2, (psf_xyz[2] - 1) // 2, lib.supported_fft_lengths())
+    ry, rz = rank // pz, rank % pz
+    rank_of = lambda a, b: a * pz + b
+    ylo, yhi = sharding.slab_range(ny, py, ry)
+    lo, hi = sharding.slab_range(nz, pz, rz)
+    y0, y1 = sharding.extended_range(ylo, yhi, ny, Hy)
+    z0, z1 = sharding.extended_range(lo, hi, nz, Hz)
 
-    psfs, imgs, weights, psi0, maxv = make_slab_inputs(torch, lib, name, z0, z1, local)
+    psfs, imgs, weights, psi0, maxv = make_box_inputs(torch, lib, name, y0, y1, z0, z1, local)
     if world > 1:                                            # the per-view maximum is a global quantity
         mt = torch.tensor(maxv, device=f"cuda:{local}")
         dist.all_reduce(mt, op=dist.ReduceOp.MAX)
         maxv = [float(x) for x in mt.tolist()]
-    shard = None if world == 1 else (lo, hi, z0, z1 - z0)
+    shard = None if pz == 1 else (lo, hi, z0, z1 - z0)
+    shard_y = None if py == 1 else (ylo, yhi, y0, y1 - y0)
 
     def build(views_data):
         views = [m.DeconView(im, w, psfs[v], m.PSFTYPE(ptype)) for v, (im, w) in enumerate(views_data)]
-        return m.DeconViews(views, device=local, lambda_=lam, shard=shard, global_dims_zyx=dims)
+        return m.DeconViews(views, device=local, lambda_=lam, shard=shard, shard_y=shard_y, global_dims_zyx=dims)
 
     # ---------------- kernel-only leg: everything resident --------------------------------------------------------
     dv = build([(m.DeviceArray.from_torch(im), m.DeviceArray.from_torch(w)) for im, w in zip(imgs, weights)])
@@ -308,16 +316,16 @@ def run_ours(args):
     psi0_host = psi0.cpu().numpy()
     dec = m.MultiViewDeconvolutionSeq(dv, 0, m.PsiInitFromRAI(psi0_host, maxv))
     stream = torch.cuda.ExternalStream(dv.stream_handle(), device=f"cuda:{local}")
-    plane = ny * nx
+    plane = (y1 - y0) * nx
 
     def exchange():
-        """halo exchange of the freshly updated psi with the z-neighbours (NCCL send/recv over NVLink)"""
+        """halo exchange of the freshly updated psi with the y / z neighbours (NCCL send/recv over NVLink).  Everything is ordered on
+        the context's stream (no host synchronisation): the NCCL work waits for the update kernels, the next update waits for NCCL."""
         if world == 1:
             return
-        dv.synchronize()
-        buf = torch.as_tensor(m.RawDeviceBuffer(dv.psi_device_ptr(), ((z1 - z0) * plane,)), device=f"cuda:{local}")
-        sharding.exchange_halos(buf, plane, lo, hi, z0, H, rank, world, dist)
-        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            buf = torch.as_tensor(m.RawDeviceBuffer(dv.psi_device_ptr(), (z1 - z0, y1 - y0, nx)), device=f"cuda:{local}")
+            sharding.exchange_halos_2d(buf, (ylo, yhi), (y0, y1 - y0), (lo, hi), (z0, z1 - z0), Hy, Hz, ry, rz, py, pz, rank_of, dist)
 
     def one_iteration():
         for v in range(V):
@@ -380,6 +388,7 @@ def run_ours(args):
         dist.barrier()
     t0 = time.perf_counter()
     dv = build(host)                                         # H2D of all views, PSF -> kernels, spectra
+    stream = torch.cuda.ExternalStream(dv.stream_handle(), device=f"cuda:{local}")
     dec = m.MultiViewDeconvolutionSeq(dv, 0, m.PsiInitFromRAI(psi0_host, maxv))      # H2D psi
     for _ in range(e2e_iters):
         one_iteration()
@@ -402,7 +411,7 @@ def run_ours(args):
         # dominant pass = largest accumulated time
         dom = int(np.argmax(pass_ms))
         per_launch_ms = pass_ms[dom] / max(pass_n[dom], 1)
-        useful_vox_per_launch = (hi - lo) * plane / info["num_tiles"]
+        useful_vox_per_launch = (hi - lo) * (yhi - ylo) * nx / info["num_tiles"]
         achieved = PASS_BYTES[dom] * useful_vox_per_launch / (per_launch_ms * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.skip_cpu:
@@ -421,11 +430,11 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[name], "step": f"one OSEM iteration = {V} view updates over the whole volume",
                        "fft_tile_xyz": info["tile_dims_xyz"], "tiles_per_gpu": info["num_tiles"], "fft_box_over_useful_voxels": round(info["fft_volume_ratio"], 4),
-                       "sharding": "none" if world == 1 else f"z-slabs, {H}-plane psi halo exchange per view update (NCCL send/recv)",
+                       "sharding": "none" if world == 1 else f"{py} x {pz} (y x z) boxes, psi halo exchange ({Hy} rows / {Hz} planes) per view update, NCCL send/recv ordered on the compute stream",
                        "l2_flush": "not needed: every pass streams >= 1.2 GB (inputs larger than the 126 MB L2)",
                        "roofline_fraction_92B": value * B_ALG / (peak * 1e9 * world), "output_finite": finite},
             "roofline": {"bound": "hbm", "kernel": PASS_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(dom), "peak_source": peak_src, "algorithmic_bytes_per_voxel": PASS_BYTES[dom],
+                         "traffic": ncu_traffic(dom) if list(info["tile_dims_xyz"]) == [1080, 540, 540] else None, "peak_source": peak_src, "algorithmic_bytes_per_voxel": PASS_BYTES[dom],
                          "ms_per_launch": per_launch_ms, "share_of_step": pass_ms[dom] / max(sum(pass_ms), 1e-9),
                          "all_passes_ms_per_launch": [round(a / max(b, 1), 4) for a, b in zip(pass_ms, pass_n)]},
             "cpu_baseline": cpu,

@@ -82,10 +82,16 @@ typedef struct mvd_config {
      * FusionTools.java:1287-1329, Threads.java:40) is counted twice, so the reference's "normalised" kernels do not sum to 1 and
      * the result depends on the thread count.  0 = exact sum (default); T > 0 reproduces the reference run with T ImageJ threads. */
     int norm_quirk_threads;
+    /* optional second sharding axis (y), same meaning as the z fields; all zero = y is not sharded.  A 2-d (y x z) process grid keeps the
+     * redundant halo volume small: the single-GPU plan already splits y into two FFT tiles, so a 2-way y split costs nothing.            */
+    int shard_y_lo, shard_y_hi;
+    int local_y0, local_ny;
 } mvd_config;
 
 MVD_API const char* mvd_last_error(void);                     /* thread-local message of the last failing call          */
 MVD_API int mvd_version(void);
+/* FFT tile lengths compiled into the library (ascending, all 2^a 3^b 5^c); returns the count, fills at most cap entries.              */
+MVD_API int mvd_supported_fft_lengths(int* out, int cap);
 
 MVD_API int mvd_create(const mvd_config* cfg, mvd_context** out);
 MVD_API int mvd_destroy(mvd_context* ctx);
@@ -146,6 +152,7 @@ MVD_API int mvd_fetch_stats(mvd_context* ctx, int count, double* stats);
 /* Introspection for benchmarks / multi-GPU hosts */
 MVD_API int mvd_tile_info(mvd_context* ctx, int tile_dims[3], int* num_tiles, double* fft_volume_ratio, int* launches_per_view_update);
 MVD_API int mvd_halo_planes(mvd_context* ctx, int* lo, int* hi);            /* z planes needed beyond the owned slab       */
+MVD_API int mvd_halo_rows(mvd_context* ctx, int* lo, int* hi);              /* y rows needed beyond the owned box (y sharding) */
 MVD_API int mvd_psi_device_ptr(mvd_context* ctx, void** current);           /* device address of the current psi buffer    */
 MVD_API int mvd_stream_handle(mvd_context* ctx, void** cuda_stream);
 

@@ -51,7 +51,8 @@ class MvdError(RuntimeError):
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int), ("dims", C.c_int * 3), ("num_views", C.c_int), ("psf_type", C.c_int),
                 ("lambda_", C.c_float), ("min_value", C.c_float), ("shard_lo", C.c_int), ("shard_hi", C.c_int),
-                ("local_z0", C.c_int), ("local_nz", C.c_int), ("max_fft_len", C.c_int), ("norm_quirk_threads", C.c_int)]
+                ("local_z0", C.c_int), ("local_nz", C.c_int), ("max_fft_len", C.c_int), ("norm_quirk_threads", C.c_int),
+                ("shard_y_lo", C.c_int), ("shard_y_hi", C.c_int), ("local_y0", C.c_int), ("local_ny", C.c_int)]
 
 
 _F = C.POINTER(C.c_float)
@@ -70,6 +71,7 @@ SYMBOLS = {
     "getFreeMemDeviceCUDA": (C.c_longlong, [C.c_int]),
     "mvd_last_error": (C.c_char_p, []),
     "mvd_version": (C.c_int, []),
+    "mvd_supported_fft_lengths": (C.c_int, [_I, C.c_int]),
     "mvd_create": (C.c_int, [C.POINTER(_Config), C.POINTER(C.c_void_p)]),
     "mvd_destroy": (C.c_int, [C.c_void_p]),
     "mvd_set_view": (C.c_int, [C.c_void_p, C.c_int, _F, _F]),
@@ -94,6 +96,7 @@ SYMBOLS = {
     "mvd_fetch_stats": (C.c_int, [C.c_void_p, C.c_int, _D]),
     "mvd_tile_info": (C.c_int, [C.c_void_p, _I, _I, _D, _I]),
     "mvd_halo_planes": (C.c_int, [C.c_void_p, _I, _I]),
+    "mvd_halo_rows": (C.c_int, [C.c_void_p, _I, _I]),
     "mvd_psi_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "mvd_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "mvd_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
@@ -144,6 +147,12 @@ class Lib:
         imdim = (C.c_int * 3)(*im.shape)          # {z,y,x}, CUDATools.getCUDACoordinates (CUDATools.java:41-49)
         kdim = (C.c_int * 3)(*k.shape)
         self.dll.convolution3DfftCUDAInPlace(_fp(im), imdim, _fp(k), kdim, int(devCUDA))
+
+    def supported_fft_lengths(self) -> List[int]:
+        n = self.dll.mvd_supported_fft_lengths(None, 0)
+        buf = (C.c_int * n)()
+        self.dll.mvd_supported_fft_lengths(buf, n)
+        return list(buf)
 
     def getNumDevicesCUDA(self) -> int:
         return int(self.dll.getNumDevicesCUDA())
@@ -272,6 +281,7 @@ class DeconViews:
 
     def __init__(self, views: Sequence[DeconView], device: int = 0, lambda_: float = 0.0, min_value: float = minValue,
                  shard: Optional[Tuple[int, int, int, int]] = None, global_dims_zyx: Optional[Sequence[int]] = None,
+                 shard_y: Optional[Tuple[int, int, int, int]] = None,
                  max_fft_len: int = 0, norm_quirk_threads: int = 0, library: Optional[Lib] = None):
         self.lib = library or lib()
         self.views = list(views)
@@ -296,6 +306,8 @@ class DeconViews:
         cfg.min_value = float(min_value)
         if shard is not None:
             cfg.shard_lo, cfg.shard_hi, cfg.local_z0, cfg.local_nz = (int(x) for x in shard)
+        if shard_y is not None:
+            cfg.shard_y_lo, cfg.shard_y_hi, cfg.local_y0, cfg.local_ny = (int(x) for x in shard_y)
         cfg.max_fft_len = int(max_fft_len)
         cfg.norm_quirk_threads = int(norm_quirk_threads)      # 0 = exact sums; T reproduces AdjustInput.sumImg for T threads
         self._ctx = C.c_void_p()
@@ -385,6 +397,11 @@ class DeconViews:
     def halo_planes(self):
         lo, hi = C.c_int(), C.c_int()
         self.lib.check(self.lib.dll.mvd_halo_planes(self._ctx, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def halo_rows(self):
+        lo, hi = C.c_int(), C.c_int()
+        self.lib.check(self.lib.dll.mvd_halo_rows(self._ctx, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
 
     def close(self):

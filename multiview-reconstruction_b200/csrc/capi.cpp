@@ -50,6 +50,11 @@ extern "C" {
 
 const char* mvd_last_error(void) { return g_last_error.c_str(); }
 int mvd_version(void) { return 100; }
+int mvd_supported_fft_lengths(int* out, int cap) {
+    const std::vector<int>& v = supported_lengths();
+    for (int i = 0; i < (int)v.size() && i < cap && out; ++i) out[i] = v[i];
+    return (int)v.size();
+}
 
 int mvd_create(const mvd_config* cfg, mvd_context** out) {
     return guarded([&] {
@@ -72,6 +77,9 @@ int mvd_create(const mvd_config* cfg, mvd_context** out) {
         if (shi <= slo) { slo = 0; shi = cfg->dims[2]; }
         if (nz <= 0) { z0 = 0; nz = cfg->dims[2]; }
         g.own_lo[2] = slo; g.own_hi[2] = shi; g.goff[2] = z0; g.vol[2] = nz;
+        if (cfg->shard_y_hi > cfg->shard_y_lo && cfg->local_ny > 0) {
+            g.own_lo[1] = cfg->shard_y_lo; g.own_hi[1] = cfg->shard_y_hi; g.goff[1] = cfg->local_y0; g.vol[1] = cfg->local_ny;
+        }
         mvd_context* ctx = new mvd_context();
         try { ctx->engine = new Engine(c); } catch (...) { delete ctx; throw; }
         *out = ctx;
@@ -196,6 +204,15 @@ int mvd_halo_planes(mvd_context* ctx, int* lo, int* hi) {
         require(ctx && ctx->engine->convolver(), "views not initialised");
         if (lo) *lo = ctx->halo_lo;
         if (hi) *hi = ctx->halo_hi;
+    });
+}
+int mvd_halo_rows(mvd_context* ctx, int* lo, int* hi) {
+    return guarded([&] {
+        require(ctx && ctx->engine->convolver(), "views not initialised");
+        int l, h;
+        ctx->engine->halo_needed_y(l, h);
+        if (lo) *lo = l;
+        if (hi) *hi = h;
     });
 }
 int mvd_psi_device_ptr(mvd_context* ctx, void** current) {

@@ -539,6 +539,10 @@ void Engine::init_views() {
     halo_hi_ = cfg_.geom.own_hi[2] == cfg_.geom.gdim[2] ? 0 : r1[2].hi + r2[2].hi;
     if (cfg_.geom.own_lo[2] - halo_lo_ < cfg_.geom.goff[2] || cfg_.geom.own_hi[2] + halo_hi_ > cfg_.geom.goff[2] + cfg_.geom.vol[2])
         throw Error("sharded context: the local arrays do not contain the halo planes (k1z/2 + k2z/2 per interior side)");
+    halo_y_lo_ = cfg_.geom.own_lo[1] == 0 ? 0 : r1[1].lo + r2[1].lo;
+    halo_y_hi_ = cfg_.geom.own_hi[1] == cfg_.geom.gdim[1] ? 0 : r1[1].hi + r2[1].hi;
+    if (cfg_.geom.own_lo[1] - halo_y_lo_ < cfg_.geom.goff[1] || cfg_.geom.own_hi[1] + halo_y_hi_ > cfg_.geom.goff[1] + cfg_.geom.vol[1])
+        throw Error("sharded context: the local arrays do not contain the halo rows (k1y/2 + k2y/2 per interior side)");
     for (View& vw : views_) { dev::free_(vw.k1hat); dev::free_(vw.k2hat); vw.k1hat = vw.k2hat = nullptr; }
     conv_.reset(new Convolver(cfg_.geom, r1, r2, 0, cfg_.max_len, stream_, tables_.get()));
     for (View& vw : views_) {
@@ -597,6 +601,7 @@ void Engine::psi_init(int type, double sigma, double* avg_out, float* max_out) {
     if (V > MVD_MAX_VIEWS) throw Error("too many views for the device PsiInit");
     const Geometry& g = cfg_.geom;
     const bool sharded = g.own_lo[2] != 0 || g.own_hi[2] != g.gdim[2];
+    if (g.own_lo[1] != 0 || g.own_hi[1] != g.gdim[1]) throw Error("device PsiInit supports z-slab sharding only; initialise psi from the host on a y-sharded context");
     const long long plane = (long long)g.vol[0] * g.vol[1], n = (long long)local_voxels();
     const long long own0 = (long long)(g.own_lo[2] - g.goff[2]) * plane, own1 = (long long)(g.own_hi[2] - g.goff[2]) * plane;
     ViewPtrs vp;
@@ -714,6 +719,7 @@ void Engine::iteration_mul() {
     const int V = cfg_.num_views;
     if (V > MVD_MAX_VIEWS) throw Error("too many views");
     const Geometry& g = cfg_.geom;
+    if (g.own_lo[1] != 0 || g.own_hi[1] != g.gdim[1]) throw Error("the Mul iteration supports z-slab sharding only");
     const long long plane = (long long)g.vol[0] * g.vol[1], n = (long long)local_voxels();
     const long long own0 = (long long)(g.own_lo[2] - g.goff[2]) * plane, own1 = (long long)(g.own_hi[2] - g.goff[2]) * plane;
     if ((int)integral_.size() < V) {

@@ -190,6 +190,7 @@ class Engine {
     int launches_per_view_update() const;
     // z planes beyond the owned slab whose psi / image values the two chained convolutions actually read
     void halo_needed(int& lo, int& hi) const { lo = halo_lo_; hi = halo_hi_; }
+    void halo_needed_y(int& lo, int& hi) const { lo = halo_y_lo_; hi = halo_y_hi_; }
 
   private:
     struct View {
@@ -214,7 +215,7 @@ class Engine {
     float* psi_[2] = {nullptr, nullptr};
     int cur_ = 0;
     bool inited_ = false;
-    int halo_lo_ = 0, halo_hi_ = 0;
+    int halo_lo_ = 0, halo_hi_ = 0, halo_y_lo_ = 0, halo_y_hi_ = 0;
     // statistics
     double* part_sum_ = nullptr;
     float* part_max_ = nullptr;

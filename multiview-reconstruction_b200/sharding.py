@@ -35,3 +35,89 @@ def exchange_halos(buf, plane: int, lo: int, hi: int, z0: int, halo: int, rank: 
         ops.append(dist.P2POp(dist.irecv, buf[(hi - z0) * plane:(hi - z0 + halo) * plane], rank + 1))
     for req in dist.batch_isend_irecv(ops):
         req.wait()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2-d (y x z) process grid
+# ---------------------------------------------------------------------------------------------------------------------
+def axis_cost(n: int, lo: int, hi: int, reach: int, lengths) -> int:
+    """FFT-box extent (tiles * T) the engine's planner needs to cover [lo, hi) of an axis of size n when each of the two chained
+    convolutions reaches `reach` samples (mirrors plan_axis in csrc/engine.cpp; halo per interior side = 2 * reach)."""
+    best = None
+    for T in lengths:
+        pos, o, tiles, ok = lo, (-reach if lo == 0 else lo - 2 * reach), 0, True
+        while pos < hi:
+            vend = o + T - 2 * reach
+            if hi == n and o + T >= n + reach:
+                vend = hi
+            nxt = min(vend, hi)
+            if nxt <= pos:
+                ok = False
+                break
+            tiles += 1
+            pos, o = nxt, nxt - 2 * reach
+        if ok and (best is None or tiles * T < best):
+            best = tiles * T
+    if best is None:
+        raise ValueError("no FFT length fits")
+    return best
+
+
+def grid_for(world: int, ny: int, nz: int, reach_y: int, reach_z: int, lengths) -> Tuple[int, int]:
+    """(py, pz) with py * pz == world minimising the FFT-box volume of the slowest rank, evaluated with the library's real tile
+    lengths (Lib.supported_fft_lengths()).  At equal cost the larger py wins: the single-GPU plan already splits y into FFT tiles,
+    so the first y split is free."""
+    best = None
+    for py in range(1, world + 1):
+        if world % py:
+            continue
+        pz = world // py
+        if ny // py <= 4 * reach_y or nz // pz <= 4 * reach_z:
+            continue
+        cy = max(axis_cost(ny, *slab_range(ny, py, r), reach_y, lengths) for r in range(py))
+        cz = max(axis_cost(nz, *slab_range(nz, pz, r), reach_z, lengths) for r in range(pz))
+        key = (cy * cz, -py)
+        if best is None or key < best[0]:
+            best = (key, (py, pz))
+    if best is None:
+        raise ValueError("volume too small for this many ranks")
+    return best[1]
+
+
+def exchange_halos_2d(buf3, own_y, loc_y, own_z, loc_z, halo_y, halo_z, ry, rz, py, pz, rank_of, dist) -> None:
+    """buf3: tensor [nz_loc, ny_loc, nx] of the extended local box holding the updated psi on the owned box.
+    Phase 1 exchanges y rows over the owned z planes, phase 2 exchanges z planes INCLUDING the freshly received y halos, so the
+    corner regions are correct.  own_* = (lo, hi) global, loc_* = (start, size) of the local array along that axis."""
+    ylo, yhi = own_y
+    y0 = loc_y[0]
+    zlo, zhi = own_z
+    z0 = loc_z[0]
+    if py > 1:
+        zs = slice(zlo - z0, zhi - z0)
+        ops, recvs = [], []
+        if ry > 0:
+            peer = rank_of(ry - 1, rz)
+            send = buf3[zs, ylo - y0:ylo - y0 + halo_y, :].contiguous()
+            rb = buf3.new_empty(send.shape)
+            ops += [dist.P2POp(dist.isend, send, peer), dist.P2POp(dist.irecv, rb, peer)]
+            recvs.append((rb, slice(ylo - y0 - halo_y, ylo - y0)))
+        if ry < py - 1:
+            peer = rank_of(ry + 1, rz)
+            send = buf3[zs, yhi - y0 - halo_y:yhi - y0, :].contiguous()
+            rb = buf3.new_empty(send.shape)
+            ops += [dist.P2POp(dist.isend, send, peer), dist.P2POp(dist.irecv, rb, peer)]
+            recvs.append((rb, slice(yhi - y0, yhi - y0 + halo_y)))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for rb, ys in recvs:
+            buf3[zs, ys, :] = rb
+    if pz > 1:
+        ops = []
+        if rz > 0:
+            peer = rank_of(ry, rz - 1)
+            ops += [dist.P2POp(dist.isend, buf3[zlo - z0:zlo - z0 + halo_z], peer), dist.P2POp(dist.irecv, buf3[zlo - z0 - halo_z:zlo - z0], peer)]
+        if rz < pz - 1:
+            peer = rank_of(ry, rz + 1)
+            ops += [dist.P2POp(dist.isend, buf3[zhi - z0 - halo_z:zhi - z0], peer), dist.P2POp(dist.irecv, buf3[zhi - z0:zhi - z0 + halo_z], peer)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()

@@ -140,3 +140,40 @@ def test_sharded_matches_unsharded(hostemu_lib, oracle):
             assert dec.lib.dll.mvd_set_psi(d._ctx, np.ascontiguousarray(full[z0:z1]).ctypes.data_as(m._F)) == 0
     for d, *_ in shards:
         d.close()
+
+
+def test_2d_sharding_y_and_z_matches_unsharded(hostemu_lib, oracle):
+    """(y x z) = 2 x 2 process grid emulated in one process: every shard owns a box, halos are refreshed from the assembled volume."""
+    import mvrecon_b200 as m
+    dims = (40, 44, 36)
+    ds = oracle.make_synthetic(dims, 2, seed=4, psf_size_xyz=(5, 5, 5), psf_sigma_xyz=(1.0, 1.0, 1.2), bead_density=1024)
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN)
+    mx = [v.max_intensity for v in views]
+    nz, ny, nx = dims
+    H = 4
+    shards = []
+    for (ylo, yhi) in [(0, 22), (22, 44)]:
+        for (zlo, zhi) in [(0, 20), (20, 40)]:
+            y0, y1, z0, z1 = max(0, ylo - H), min(ny, yhi + H), max(0, zlo - H), min(nz, zhi + H)
+            loc = [m.DeconView(np.ascontiguousarray(ds.images[v][z0:z1, y0:y1]), np.ascontiguousarray(ds.weights[v][z0:z1, y0:y1]),
+                               ds.psfs[v], m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(2)]
+            d = m.DeconViews(loc, shard=(zlo, zhi, z0, z1 - z0), shard_y=(ylo, yhi, y0, y1 - y0), global_dims_zyx=dims, library=hostemu_lib)
+            assert d.halo_rows() == ((0 if ylo == 0 else H), (0 if yhi == ny else H))
+            dec = m.MultiViewDeconvolutionSeq(d, 0, m.PsiInitFromRAI(np.ascontiguousarray(psi0[z0:z1, y0:y1]), mx))
+            shards.append((d, dec, (ylo, yhi, y0, y1), (zlo, zhi, z0, z1)))
+    full = psi0.copy()
+    psi64 = psi0
+    for it in range(2):
+        for v in range(2):
+            new = np.empty_like(full)
+            for d, dec, (ylo, yhi, y0, y1), (zlo, zhi, z0, z1) in shards:
+                d.enqueue_view_update(v)
+                d.synchronize()
+                new[zlo:zhi, ylo:yhi] = dec.getPSI()[zlo - z0:zhi - z0, ylo - y0:yhi - y0]
+            full = new
+            psi64, _, _ = oracle.view_update_whole(psi64, views[v], 0.0, dtype=np.float64)
+            assert oracle.rel_l2(full, psi64) < 4e-6
+            for d, dec, (ylo, yhi, y0, y1), (zlo, zhi, z0, z1) in shards:
+                assert d.lib.dll.mvd_set_psi(d._ctx, np.ascontiguousarray(full[z0:z1, y0:y1]).ctypes.data_as(m._F)) == 0
+    for d, *_ in shards:
+        d.close()

@@ -68,3 +68,47 @@ def test_slab_ranges_cover_the_volume():
         assert r[0][0] == 0 and r[-1][1] == nz and all(r[i][1] == r[i + 1][0] for i in range(world - 1))
     assert sharding.extended_range(64, 128, 512, 24) == (40, 152)
     assert sharding.extended_range(0, 64, 512, 24) == (0, 88)
+
+
+def _worker2d(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from mvrecon_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nz, ny, nx, hy, hz, py, pz = 24, 28, 5, 3, 2, 2, 2
+    ry, rz = rank // pz, rank % pz
+    rank_of = lambda a, b: a * pz + b
+    glob = torch.arange(nz * ny * nx, dtype=torch.float32).reshape(nz, ny, nx)
+    ylo, yhi = sharding.slab_range(ny, py, ry)
+    zlo, zhi = sharding.slab_range(nz, pz, rz)
+    y0, y1 = sharding.extended_range(ylo, yhi, ny, hy)
+    z0, z1 = sharding.extended_range(zlo, zhi, nz, hz)
+    loc = torch.full((z1 - z0, y1 - y0, nx), -1.0)
+    loc[zlo - z0:zhi - z0, ylo - y0:yhi - y0] = glob[zlo:zhi, ylo:yhi]          # only the owned box is known
+    sharding.exchange_halos_2d(loc, (ylo, yhi), (y0, y1 - y0), (zlo, zhi), (z0, z1 - z0), hy, hz, ry, rz, py, pz, rank_of, dist)
+    ok = bool(torch.equal(loc, glob[z0:z1, y0:y1]))                              # halos AND corners filled from the neighbours
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([ok]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_2d_halo_exchange_fills_halos_and_corners(tmp_path):
+    import torch.multiprocessing as mp
+    world = 4
+    port = 31500 + (os.getpid() % 2000)
+    mp.start_processes(_worker2d, args=(world, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    assert all(bool(np.load(tmp_path / f"ok{r}.npy")[0]) for r in range(world))
+
+
+def test_process_grid_prefers_y_first():
+    sys.path.insert(0, ROOT)
+    from mvrecon_b200 import sharding
+    lengths = [32, 64, 120, 128, 180, 192, 256, 270, 288, 300, 320, 360, 512, 540, 576, 1024, 1080, 1152]
+    assert sharding.grid_for(1, 1024, 512, 9, 12, lengths) == (1, 1)
+    assert sharding.grid_for(2, 1024, 512, 9, 12, lengths) == (2, 1)          # the single-GPU plan already splits y in two tiles
+    py, pz = sharding.grid_for(8, 1024, 512, 9, 12, lengths)
+    assert py * pz == 8 and py >= 2
+    assert sharding.axis_cost(1024, 0, 1024, 9, lengths) == 1080 and sharding.axis_cost(512, 0, 512, 12, lengths) == 540
