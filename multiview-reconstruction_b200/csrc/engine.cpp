@@ -67,8 +67,12 @@ AxisTiling plan_axis(int gdim, int a, int b, Reach r1, Reach r2, bool is_x, int 
     const int Lsum = r1.lo + r2.lo, Rsum = r1.hi + r2.hi;
     const int Lmax = std::max(r1.lo, r2.lo), Rmax = std::max(r1.hi, r2.hi);
     AxisTiling best;
+    static const int force_x = [] { const char* e = std::getenv("MVD_FORCE_XLEN"); return e ? std::atoi(e) : 0; }();       // experiments only
+    static const int exclude_x = [] { const char* e = std::getenv("MVD_EXCLUDE_XLEN"); return e ? std::atoi(e) : 0; }();   // experiments only
     for (int len : supported_lengths()) {
         if (len > max_len) break;
+        if (is_x && len == exclude_x) continue;
+        if (is_x && force_x && len != force_x) continue;
         const int T = is_x ? 2 * len : len;
         AxisTiling cur;
         cur.T = T;

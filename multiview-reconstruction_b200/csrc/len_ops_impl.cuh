@@ -12,7 +12,10 @@ constexpr int min_blocks_for(size_t smem_bytes, int threads, int want) {
     int by_thr = 2048 / threads;
     int b = by_smem < by_thr ? by_smem : by_thr;
     if (b > want) b = want;
-    while (b > 1 && 65536 / (threads * b) < 64) --b;
+#ifndef MVD_MIN_REGS
+#define MVD_MIN_REGS 64
+#endif
+    while (b > 1 && 65536 / (threads * b) < MVD_MIN_REGS) --b;
     return b < 1 ? 1 : b;
 }
 template <class P> constexpr int col_min_blocks() { return min_blocks_for(ColSmem<P>::bytes(), P::THREADS, 3); }

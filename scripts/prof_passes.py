@@ -33,7 +33,21 @@ def main():
     psfs = [o.synth_psf(v, nviews, psf_xyz) for v in range(nviews)]
     base = (100.0 + 50.0 * rng.random(dims, dtype=np.float32)).astype(np.float32)
     w = np.full(dims, 1.0 / nviews, dtype=np.float32)
-    dv = m.DeconViews([m.DeconView(base, w, psfs[v], m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(nviews)], lambda_=lam, max_fft_len=max_len)
+    imgs = [base] * nviews
+    ws = [w] * nviews
+    if os.environ.get("MVD_REALISTIC"):           # coverage gaps like the bench data: zero image / zero weight slabs, graded weights
+        imgs, ws = [], []
+        for v in range(nviews):
+            im = base.copy(); wv = w.copy()
+            sl = [slice(None)] * 3
+            ax = (v % 6) // 2
+            cut = dims[ax] // 8
+            sl[ax] = slice(0, cut) if v % 2 == 0 else slice(dims[ax] - cut, dims[ax])
+            im[tuple(sl)] = 0; wv[tuple(sl)] = 0
+            ramp = np.linspace(0, 1, dims[2], dtype=np.float32)
+            wv *= ramp[None, None, :]
+            imgs.append(im); ws.append(wv)
+    dv = m.DeconViews([m.DeconView(imgs[v], ws[v], psfs[v], m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(nviews)], lambda_=lam, max_fft_len=max_len)
     info = dv.tile_info()
     dec = m.MultiViewDeconvolutionSeq(dv, 1, m.PsiInitFromRAI(base, [200.0] * nviews))
     dec.runIterations()
