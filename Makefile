@@ -21,17 +21,17 @@ HDRS      := $(CSRC)/fft_codelets.cuh $(CSRC)/fft_passes.cuh $(CSRC)/backend.h $
 
 LENS      := $(shell MVD_LENGTHS="$(MVD_LENGTHS)" python3 $(CSRC)/gen_lengths.py $(GEN))
 LENOBJ    := $(foreach n,$(LENS),$(BUILD)/obj/len_$(n).o)
-OBJ       := $(LENOBJ) $(BUILD)/obj/registry.o $(BUILD)/obj/engine.o $(BUILD)/obj/pointwise.o $(BUILD)/obj/capi.o
+OBJ       := $(LENOBJ) $(BUILD)/obj/registry.o $(BUILD)/obj/engine.o $(BUILD)/obj/pointwise.o $(BUILD)/obj/comm.o $(BUILD)/obj/capi.o
 
 HLENS     := $(shell MVD_LENGTHS="$(HOSTEMU_LENGTHS)" python3 $(CSRC)/gen_lengths.py $(GENH))
 HLENOBJ   := $(foreach n,$(HLENS),$(BUILD)/hostemu/obj/len_$(n).o)
-HOBJ      := $(HLENOBJ) $(BUILD)/hostemu/obj/registry.o $(BUILD)/hostemu/obj/engine.o $(BUILD)/hostemu/obj/pointwise.o $(BUILD)/hostemu/obj/capi.o
+HOBJ      := $(HLENOBJ) $(BUILD)/hostemu/obj/registry.o $(BUILD)/hostemu/obj/engine.o $(BUILD)/hostemu/obj/pointwise.o $(BUILD)/hostemu/obj/comm.o $(BUILD)/hostemu/obj/capi.o
 
 .PHONY: all hostemu clean fft_emu_test
 all: $(PKG)/libmvdecon.so
 
 $(PKG)/libmvdecon.so: $(OBJ)
-	$(NVCC) -shared -o $@ $(OBJ) -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -lcudart
+	$(NVCC) -shared -o $@ $(OBJ) -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -lcudart -ldl
 
 $(BUILD)/obj/len_%.o: $(GEN)/len_%.cu $(HDRS)
 	@mkdir -p $(BUILD)/obj $(BUILD)/ptxas
@@ -45,6 +45,9 @@ $(BUILD)/obj/engine.o: $(CSRC)/engine.cpp $(HDRS)
 $(BUILD)/obj/pointwise.o: $(CSRC)/pointwise.cpp $(HDRS)
 	@mkdir -p $(BUILD)/obj
 	$(NVCC) $(NVFLAGS) -I$(CSRC) -x cu -c $< -o $@ 2> $(BUILD)/ptxas_pointwise.log || (cat $(BUILD)/ptxas_pointwise.log; false)
+$(BUILD)/obj/comm.o: $(CSRC)/comm.cpp $(HDRS)
+	@mkdir -p $(BUILD)/obj
+	$(NVCC) $(NVFLAGS) -I$(CSRC) -x cu -c $< -o $@ 2> $(BUILD)/ptxas_comm.log || (cat $(BUILD)/ptxas_comm.log; false)
 $(BUILD)/obj/capi.o: $(CSRC)/capi.cpp $(HDRS)
 	@mkdir -p $(BUILD)/obj
 	$(NVCC) $(NVFLAGS) -I$(CSRC) -x cu -c $< -o $@ 2> $(BUILD)/ptxas_capi.log || (cat $(BUILD)/ptxas_capi.log; false)
@@ -62,6 +65,9 @@ $(BUILD)/hostemu/obj/engine.o: $(CSRC)/engine.cpp $(HDRS)
 	@mkdir -p $(BUILD)/hostemu/obj
 	$(CXX) $(HOSTFLAGS) -x c++ -c $< -o $@
 $(BUILD)/hostemu/obj/pointwise.o: $(CSRC)/pointwise.cpp $(HDRS)
+	@mkdir -p $(BUILD)/hostemu/obj
+	$(CXX) $(HOSTFLAGS) -x c++ -c $< -o $@
+$(BUILD)/hostemu/obj/comm.o: $(CSRC)/comm.cpp $(HDRS)
 	@mkdir -p $(BUILD)/hostemu/obj
 	$(CXX) $(HOSTFLAGS) -x c++ -c $< -o $@
 $(BUILD)/hostemu/obj/capi.o: $(CSRC)/capi.cpp $(HDRS)

@@ -168,45 +168,56 @@ def make_box_inputs(torch, lib, name, y0, y1, z0, z1, device):
 
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region (in-process NVML, 10 ms period; nvidia-smi fallback)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
     def __init__(self, device):
         self.device = device
-        self.rows = []
-        self.proc = None
+        self.sm, self.mask, self.max_mhz = [], 0, None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nvml = None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.device]) if vis and vis.split(",")[0].isdigit() else self.device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.nvml = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _loop(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
+        if self.nvml is None:
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                q = "clocks.sm,clocks.max.sm"
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": ["nvml unavailable: single nvidia-smi sample after the region"], "samples": 1}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        self.stop_flag.set()
+        self.thread.join(timeout=1.0)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.sm)}
 
 
 def measured_peak():
@@ -327,10 +338,23 @@ def run_ours(args):
             buf = torch.as_tensor(m.RawDeviceBuffer(dv.psi_device_ptr(), (z1 - z0, y1 - y0, nx)), device=f"cuda:{local}")
             sharding.exchange_halos_2d(buf, (ylo, yhi), (y0, y1 - y0), (lo, hi), (z0, z1 - z0), Hy, Hz, ry, rz, py, pz, rank_of, dist)
 
+    use_lib_comm = world > 1 and os.environ.get("BENCH_EXCHANGE", "lib") == "lib"
+
+    def attach_comm(ctx):
+        """in-library halo exchange: NCCL send/recv enqueued on the compute stream after every view update"""
+        if not use_lib_comm:
+            return
+        ids = [lib.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(ids[0], world, rank, py, pz)
+
     def one_iteration():
         for v in range(V):
-            dv.enqueue_view_update(v)
-            exchange()
+            dv.enqueue_view_update(v)            # with a communicator attached the library exchanges the halos itself
+            if not use_lib_comm:
+                exchange()
+
+    attach_comm(dv)
 
     for _ in range(args.warmup):
         one_iteration()
@@ -389,6 +413,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     dv = build(host)                                         # H2D of all views, PSF -> kernels, spectra
     stream = torch.cuda.ExternalStream(dv.stream_handle(), device=f"cuda:{local}")
+    attach_comm(dv)
     dec = m.MultiViewDeconvolutionSeq(dv, 0, m.PsiInitFromRAI(psi0_host, maxv))      # H2D psi
     for _ in range(e2e_iters):
         one_iteration()
@@ -430,7 +455,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[name], "step": f"one OSEM iteration = {V} view updates over the whole volume",
                        "fft_tile_xyz": info["tile_dims_xyz"], "tiles_per_gpu": info["num_tiles"], "fft_box_over_useful_voxels": round(info["fft_volume_ratio"], 4),
-                       "sharding": "none" if world == 1 else f"{py} x {pz} (y x z) boxes, psi halo exchange ({Hy} rows / {Hz} planes) per view update, NCCL send/recv ordered on the compute stream",
+                       "sharding": "none" if world == 1 else f"{py} x {pz} (y x z) boxes, psi halo exchange ({Hy} rows / {Hz} planes) per view update, NCCL send/recv enqueued on the compute stream " + ("by the library" if use_lib_comm else "by torch.distributed"),
                        "l2_flush": "not needed: every pass streams >= 1.2 GB (inputs larger than the 126 MB L2)",
                        "roofline_fraction_92B": value * B_ALG / (peak * 1e9 * world), "output_finite": finite},
             "roofline": {"bound": "hbm", "kernel": PASS_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -452,7 +477,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(WORKLOADS))

@@ -156,6 +156,16 @@ MVD_API int mvd_halo_rows(mvd_context* ctx, int* lo, int* hi);              /* y
 MVD_API int mvd_psi_device_ptr(mvd_context* ctx, void** current);           /* device address of the current psi buffer    */
 MVD_API int mvd_stream_handle(mvd_context* ctx, void** cuda_stream);
 
+/* Multi-GPU: one process (or context) per GPU on a py x pz (y x z) grid of boxes, rank = ry * pz + rz (mvd_config.shard_* describe the
+ * box).  mvd_comm_unique_id: rank 0 creates a 128-byte NCCL id that the host distributes with its own plumbing; mvd_comm_init
+ * (after mvd_init_views, collective) attaches a communicator.  From then on every view update / Mul iteration is followed by the halo
+ * exchange of the new psi (y rows first, then z planes including the fresh y halos), enqueued on the context's stream -- so
+ * mvd_run_iterations works unchanged across GPUs.  mvd_exchange_halos triggers one exchange explicitly (e.g. after mvd_set_psi).
+ * NCCL is loaded with dlopen on first use; single-GPU use needs no NCCL.                                                              */
+MVD_API int mvd_comm_unique_id(char id_out[128]);
+MVD_API int mvd_comm_init(mvd_context* ctx, const char id[128], int world, int rank, int py, int pz);
+MVD_API int mvd_exchange_halos(mvd_context* ctx);
+
 /* Per-pass device timing (CUDA events on the context's stream around every pass launch): slots 0..8 = passes P1..P9 of a
  * view update.  ms[] are accumulated milliseconds, counts[] the number of launches; reset != 0 clears them.   */
 MVD_API int mvd_set_profiling(mvd_context* ctx, int on);

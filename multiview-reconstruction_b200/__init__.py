@@ -99,6 +99,9 @@ SYMBOLS = {
     "mvd_halo_rows": (C.c_int, [C.c_void_p, _I, _I]),
     "mvd_psi_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "mvd_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mvd_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "mvd_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mvd_exchange_halos": (C.c_int, [C.c_void_p]),
     "mvd_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "mvd_get_pass_times": (C.c_int, [C.c_void_p, _D, C.POINTER(C.c_longlong), C.c_int]),
     "mvd_convolve": (C.c_int, [C.c_int, _F, _I, _F, _I, C.c_int, C.c_float, _F]),
@@ -153,6 +156,11 @@ class Lib:
         buf = (C.c_int * n)()
         self.dll.mvd_supported_fft_lengths(buf, n)
         return list(buf)
+
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self.check(self.dll.mvd_comm_unique_id(buf))
+        return buf.raw
 
     def getNumDevicesCUDA(self) -> int:
         return int(self.dll.getNumDevicesCUDA())
@@ -387,6 +395,13 @@ class DeconViews:
         p = C.c_void_p()
         self.lib.check(self.lib.dll.mvd_stream_handle(self._ctx, C.byref(p)))
         return int(p.value or 0)
+
+    def comm_init(self, unique_id: bytes, world: int, rank: int, py: int, pz: int):
+        """attach the in-library NCCL halo exchange (collective over all ranks of the (y x z) grid, rank = ry * pz + rz)"""
+        self.lib.check(self.lib.dll.mvd_comm_init(self._ctx, C.create_string_buffer(bytes(unique_id), 128), int(world), int(rank), int(py), int(pz)))
+
+    def exchange_halos(self):
+        self.lib.check(self.lib.dll.mvd_exchange_halos(self._ctx))
 
     def enqueue_view_update(self, v: int):
         self.lib.check(self.lib.dll.mvd_enqueue_view_update(self._ctx, int(v)))

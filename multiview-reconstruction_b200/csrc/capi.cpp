@@ -222,6 +222,15 @@ int mvd_stream_handle(mvd_context* ctx, void** s) {
     return guarded([&] { require(ctx && s, "null argument"); *s = (void*)ctx->engine->stream(); });
 }
 
+int mvd_comm_unique_id(char id_out[128]) {
+    return guarded([&] { require(id_out != nullptr, "null argument"); HaloComm::unique_id(id_out); });
+}
+int mvd_comm_init(mvd_context* ctx, const char id[128], int world, int rank, int py, int pz) {
+    return guarded([&] { require(ctx && id, "null argument"); ctx->engine->comm_init(id, world, rank, py, pz); });
+}
+int mvd_exchange_halos(mvd_context* ctx) {
+    return guarded([&] { require(ctx, "null context"); ctx->engine->exchange_halos(); });
+}
 int mvd_set_profiling(mvd_context* ctx, int on) {
     return guarded([&] { require(ctx && ctx->engine->convolver(), "views not initialised"); ctx->engine->convolver()->set_profiling(on != 0); });
 }

@@ -426,6 +426,7 @@ Engine::~Engine() {
     }
     dev::free_(psi_[0]); dev::free_(psi_[1]);
     dev::free_(part_sum_); dev::free_(part_max_); dev::free_(stats_dev_);
+    comm_.reset();
     for (float* p : integral_) dev::free_(p);
     dev::free_(lut_dev_); dev::free_(acc_dev_); dev::free_(max_dev_);
     conv_.reset();
@@ -747,6 +748,7 @@ void Engine::iteration_mul() {
                 stats_dev_ + 2 * (size_t)stats_count_, max_dev_);
     ++stats_count_;
     cur_ ^= 1;
+    if (comm_) comm_->exchange(psi_[cur_]);
 }
 
 void Engine::view_update(int v) {
@@ -766,6 +768,22 @@ void Engine::view_update(int v) {
     pfor(1, r2, stream_);
     ++stats_count_;
     cur_ ^= 1;
+    if (comm_) comm_->exchange(psi_[cur_]);
+}
+
+void Engine::comm_init(const char id[128], int world, int rank, int py, int pz) {
+    if (!inited_) throw Error("init_views() must run before comm_init (the halo widths come from the kernels)");
+    dev::set_device(cfg_.device);
+    const Geometry& g = cfg_.geom;
+    const bool ysh = g.own_lo[1] != 0 || g.own_hi[1] != g.gdim[1], zsh = g.own_lo[2] != 0 || g.own_hi[2] != g.gdim[2];
+    if ((py > 1) != ysh || (pz > 1) != zsh) throw Error("process grid does not match the sharding of this context");
+    const int hy = std::max(halo_y_lo_, halo_y_hi_), hz = std::max(halo_lo_, halo_hi_);
+    comm_.reset(new HaloComm(id, world, rank, py, pz, g, hy, hz, stream_));
+}
+void Engine::exchange_halos() {
+    if (!comm_) throw Error("no communicator attached (mvd_comm_init)");
+    dev::set_device(cfg_.device);
+    comm_->exchange(psi_[cur_]);
 }
 
 void Engine::fetch_stats(int count, IterStats* out) {

@@ -120,6 +120,23 @@ void convolve_host(int device, stream_t s, Tables* tables, int max_len, const fl
 
 struct IterStats { double sum_change; double max_change; };
 
+// in-library halo exchange over NCCL for a (y x z) process grid (comm.cpp)
+class HaloComm {
+  public:
+    static void unique_id(char out[128]);
+    HaloComm(const char id[128], int world, int rank, int py, int pz, const Geometry& g, int halo_y, int halo_z, stream_t s);
+    ~HaloComm();
+    void exchange(float* psi);          // enqueued on the stream; the host does not block
+  private:
+    struct Impl;
+    Impl* impl_;
+    int world_, rank_, py_, pz_, ry_ = 0, rz_ = 0;
+    Geometry g_;
+    int hy_, hz_;
+    stream_t stream_;
+    float* stage_[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
 // ---- point-wise device stages (pointwise.cpp) -------------------------------------------------------------------------
 #define MVD_MAX_VIEWS 16
 struct ViewPtrs { const float* img[MVD_MAX_VIEWS]; const float* weight[MVD_MAX_VIEWS]; };
@@ -179,6 +196,9 @@ class Engine {
     void get_weight_host(int v, float* out);
     // MultiViewDeconvolutionMul.runNextIteration: one psi update from all views (geometric mean of the integrals)
     void iteration_mul();
+    // attach the NCCL halo exchange: afterwards every view update / Mul iteration is followed by the exchange of the new psi
+    void comm_init(const char id[128], int world, int rank, int py, int pz);
+    void exchange_halos();
     void view_update(int v);                               // asynchronous on the engine stream
     void fetch_stats(int count, IterStats* out);           // last `count` view updates (synchronises)
     void run_iterations(int n, IterStats* out /* n*V or null */);
@@ -221,6 +241,7 @@ class Engine {
     float* part_max_ = nullptr;
     double* stats_dev_ = nullptr;   // ring of {sum,max} pairs
     void ensure_stats_slot();
+    std::unique_ptr<HaloComm> comm_;
     std::vector<float*> integral_;  // Mul iteration: one integral volume per view
     double* lut_dev_ = nullptr;     // cosine blending LUT
     double* acc_dev_ = nullptr;     // {sum, count} scratch

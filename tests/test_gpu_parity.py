@@ -322,3 +322,48 @@ def test_fullsize_update_properties(product_lib, oracle, c2_volume):
     ref, _, _ = oracle.view_update_whole(img[sl], ov, 0.006, dtype=np.float64)
     assert oracle.rel_l2(one[z:z + s, y:y + s, x:x + s], ref[core]) <= rel_tol(1)
     assert got.shape == (s, s, s)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# scaled-down versions of the BASELINE configs c4 / c5 (the full sizes need 8 GPUs): many views, large anisotropic PSFs
+# ---------------------------------------------------------------------------------------------------------------------
+def test_c5_like_large_anisotropic_psf_optimization_ii(product_lib, oracle):
+    """7 views, OPTIMIZATION_II, anisotropic 15x15x31 PSFs tilted by 4 degree steps, 3 iterations (config c5 scaled by 1/2 in the PSF)."""
+    import mvrecon_b200 as m
+    ds = oracle.make_synthetic((96, 72, 80), 7, seed=20265, psf_size_xyz=(15, 15, 31), psf_sigma_xyz=(1.3, 1.3, 4.5), bead_density=4096,
+                               tilt_step_deg=4.0)
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.OPTIMIZATION_II)
+    dv = m.DeconViews(_views(m, ds, oracle.OPTIMIZATION_II))
+    try:
+        info = dv.tile_info()
+        dec = m.MultiViewDeconvolutionSeq(dv, 3, m.PsiInitFromRAI(psi0, [v.max_intensity for v in views]))
+        psi64 = psi0
+        for it in range(1, 4):
+            dec.runNextIteration()
+            for v in range(7):
+                psi64, _, _ = oracle.view_update_whole(psi64, views[v], 0.0, dtype=np.float64)
+            assert oracle.rel_l2(dec.getPSI(), psi64) <= rel_tol(it), (it, info)
+    finally:
+        dv.close()
+
+
+def test_c4_like_independent_eight_views_device_weights(product_lib, oracle):
+    """8 views, INDEPENDENT (classic multi-view RL, kernel2 = flipped kernel1), weight masks generated and normalised on the device."""
+    import mvrecon_b200 as m
+    ds = oracle.make_synthetic((48, 64, 72), 8, seed=20264, psf_size_xyz=(9, 7, 9), psf_sigma_xyz=(1.4, 1.2, 2.2), bead_density=2048)
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.INDEPENDENT)
+    dv = m.DeconViews([m.DeconView(ds.images[v], None, ds.psfs[v], m.PSFTYPE.INDEPENDENT) for v in range(8)])
+    try:
+        for v in range(8):
+            mn, mx = ds.boxes[v]
+            dv.makeBlendingWeights(v, mn, mx, (0.0,) * 3, (12.0,) * 3)
+        dv.normalizeWeights(1.0, False)
+        for v in range(8):
+            assert np.array_equal(dv.getWeight(v), ds.weights[v])
+        dec = m.MultiViewDeconvolutionSeq(dv, 2, m.PsiInitBlurredFused(5.0))
+        assert oracle.rel_l2(dec.getPSI(), psi0) < 1e-6
+        dec.runIterations()
+        ref, _ = oracle.run_iterations_seq(psi0, views, 2, 0.0, dtype=np.float64)
+        assert oracle.rel_l2(dec.getPSI(), ref) <= 3 * rel_tol(2)       # psi0 differs at 1e-7 (FFT Gaussian vs separable sum)
+    finally:
+        dv.close()
