@@ -101,6 +101,10 @@ MVD_API int mvd_destroy(mvd_context* ctx);
  * memory that must stay valid until mvd_destroy.                                                                       */
 MVD_API int mvd_set_view(mvd_context* ctx, int v, const float* img_host, const float* weight_host);
 MVD_API int mvd_set_view_device(mvd_context* ctx, int v, const float* img_dev, const float* weight_dev);
+/* Asynchronous variant of mvd_set_view: the copies are enqueued on a separate copy stream and the call returns immediately; the host
+ * buffers (page-locked for real overlap) must stay valid and unmodified until mvd_synchronize / mvd_get_psi / mvd_run_iterations
+ * returned.  The first update of view v waits only for view v's upload, so later uploads overlap the first iteration.                */
+MVD_API int mvd_set_view_async(mvd_context* ctx, int v, const float* img_host, const float* weight_host);
 /* DeconViewPSF( kernel, psfType ): raw PSF of view v (need not be normalised), size kdims (x,y,z), odd sizes expected.  */
 MVD_API int mvd_set_psf(mvd_context* ctx, int v, const float* psf, const int kdims[3]);
 /* alternative: hand over kernel1 / kernel2 directly (what runIteration receives, ComputeBlockSeqThread.java:54-61)      */

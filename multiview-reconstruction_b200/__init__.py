@@ -76,6 +76,7 @@ SYMBOLS = {
     "mvd_destroy": (C.c_int, [C.c_void_p]),
     "mvd_set_view": (C.c_int, [C.c_void_p, C.c_int, _F, _F]),
     "mvd_set_view_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mvd_set_view_async": (C.c_int, [C.c_void_p, C.c_int, _F, _F]),
     "mvd_set_psf": (C.c_int, [C.c_void_p, C.c_int, _F, _I]),
     "mvd_set_kernels": (C.c_int, [C.c_void_p, C.c_int, _F, _I, _F, _I]),
     "mvd_init_views": (C.c_int, [C.c_void_p]),
@@ -290,7 +291,7 @@ class DeconViews:
     def __init__(self, views: Sequence[DeconView], device: int = 0, lambda_: float = 0.0, min_value: float = minValue,
                  shard: Optional[Tuple[int, int, int, int]] = None, global_dims_zyx: Optional[Sequence[int]] = None,
                  shard_y: Optional[Tuple[int, int, int, int]] = None,
-                 max_fft_len: int = 0, norm_quirk_threads: int = 0, library: Optional[Lib] = None):
+                 max_fft_len: int = 0, norm_quirk_threads: int = 0, async_upload: bool = False, library: Optional[Lib] = None):
         self.lib = library or lib()
         self.views = list(views)
         if not self.views:
@@ -326,6 +327,8 @@ class DeconViews:
                     if not (isinstance(v.image, DeviceArray) and isinstance(v.weight, DeviceArray)):
                         raise MvdError("image and weight of a view must both be host arrays or both DeviceArrays")
                     self.lib.check(self.lib.dll.mvd_set_view_device(self._ctx, i, C.c_void_p(v.image.ptr), C.c_void_p(v.weight.ptr)))
+                elif async_upload:      # this object keeps the host arrays alive until close(); page-locked arrays overlap with compute
+                    self.lib.check(self.lib.dll.mvd_set_view_async(self._ctx, i, _fp(v.image), None if v.weight is None else _fp(v.weight)))
                 elif v.weight is None:
                     self.lib.check(self.lib.dll.mvd_set_view(self._ctx, i, _fp(v.image), None))
                 else:
@@ -528,8 +531,11 @@ class MultiViewDeconvolutionSeq:
             self.stats.append([IterationStatistics(float(st[2 * (i * V + v)]), float(st[2 * (i * V + v) + 1])) for v in range(V)])
         self.it = self.numIterations
 
-    def getPSI(self) -> np.ndarray:
-        psi = np.empty(self.views.local_shape, dtype=np.float32)
+    def getPSI(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """download psi; `out` may be a caller-provided (e.g. page-locked) float32 array of the local shape"""
+        psi = np.empty(self.views.local_shape, dtype=np.float32) if out is None else out
+        if psi.shape != tuple(self.views.local_shape) or psi.dtype != np.float32 or not psi.flags.c_contiguous:
+            raise MvdError("out must be a contiguous float32 array of the psi shape")
         self.lib.check(self.lib.dll.mvd_get_psi(self.views._ctx, _fp(psi)))
         return psi
 

@@ -55,6 +55,11 @@ inline void zero(void* d, size_t n, stream_t s) { MVD_CUDA_CHECK(cudaMemsetAsync
 inline void sync(stream_t s) { MVD_CUDA_CHECK(cudaStreamSynchronize(s)); }
 inline stream_t stream_create() { cudaStream_t s; MVD_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return s; }
 inline void stream_destroy(stream_t s) { if (s) cudaStreamDestroy(s); }
+typedef cudaEvent_t event_t;
+inline event_t event_create() { cudaEvent_t e; MVD_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); return e; }
+inline void event_destroy(event_t e) { if (e) cudaEventDestroy(e); }
+inline void event_record(event_t e, stream_t s) { MVD_CUDA_CHECK(cudaEventRecord(e, s)); }
+inline void stream_wait(stream_t s, event_t e) { MVD_CUDA_CHECK(cudaStreamWaitEvent(s, e, 0)); }
 }  // namespace dev
 
 template <class F>
@@ -94,6 +99,11 @@ inline void zero(void* d, size_t n, stream_t) { std::memset(d, 0, n); }
 inline void sync(stream_t) {}
 inline stream_t stream_create() { return nullptr; }
 inline void stream_destroy(stream_t) {}
+typedef void* event_t;
+inline event_t event_create() { return nullptr; }
+inline void event_destroy(event_t) {}
+inline void event_record(event_t, stream_t) {}
+inline void stream_wait(stream_t, event_t) {}
 }  // namespace dev
 
 template <class F>

@@ -97,6 +97,9 @@ int mvd_destroy(mvd_context* ctx) {
 int mvd_set_view(mvd_context* ctx, int v, const float* img, const float* weight) {
     return guarded([&] { require(ctx && img, "null argument"); ctx->engine->set_view_host(v, img, weight); });
 }
+int mvd_set_view_async(mvd_context* ctx, int v, const float* img, const float* weight) {
+    return guarded([&] { require(ctx && img, "null argument"); ctx->engine->set_view_host_async(v, img, weight); });
+}
 int mvd_set_view_device(mvd_context* ctx, int v, const float* img, const float* weight) {
     return guarded([&] { require(ctx && img && weight, "null argument"); ctx->engine->set_view_device(v, img, weight); });
 }

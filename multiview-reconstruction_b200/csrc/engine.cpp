@@ -421,9 +421,13 @@ Engine::Engine(const Config& c) : cfg_(c) {
 
 Engine::~Engine() {
     try { dev::set_device(cfg_.device); dev::sync(stream_); } catch (...) {}
+    if (copy_stream_) { try { dev::sync(copy_stream_); } catch (...) {} }
     for (View& v : views_) {
         dev::free_(v.img_owned); dev::free_(v.weight_owned); dev::free_(v.k1hat); dev::free_(v.k2hat);
+        dev::event_destroy(v.ready);
     }
+    small_conv_.reset();
+    dev::stream_destroy(copy_stream_);
     dev::free_(psi_[0]); dev::free_(psi_[1]);
     dev::free_(part_sum_); dev::free_(part_max_); dev::free_(stats_dev_);
     comm_.reset();
@@ -444,6 +448,23 @@ void Engine::set_view_host(int v, const float* img, const float* weight) {
     dev::h2d(vw.img_owned, img, bytes, stream_);
     if (weight) dev::h2d(vw.weight_owned, weight, bytes, stream_);       // weight == nullptr: generated on the device later
     else dev::zero(vw.weight_owned, bytes, stream_);
+    vw.img = vw.img_owned;
+    vw.weight = vw.weight_owned;
+}
+void Engine::set_view_host_async(int v, const float* img, const float* weight) {
+    if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
+    dev::set_device(cfg_.device);
+    View& vw = views_[v];
+    const size_t bytes = sizeof(float) * local_voxels();
+    if (!vw.img_owned) vw.img_owned = (float*)dev::alloc(bytes);
+    if (!vw.weight_owned) vw.weight_owned = (float*)dev::alloc(bytes);
+    if (!copy_stream_) copy_stream_ = dev::stream_create();
+    if (!vw.ready) vw.ready = dev::event_create();
+    dev::h2d(vw.img_owned, img, bytes, copy_stream_);
+    if (weight) dev::h2d(vw.weight_owned, weight, bytes, copy_stream_);
+    else dev::zero(vw.weight_owned, bytes, copy_stream_);
+    dev::event_record(vw.ready, copy_stream_);
+    vw.pending = true;
     vw.img = vw.img_owned;
     vw.weight = vw.weight_owned;
 }
@@ -472,8 +493,32 @@ void Engine::set_kernels(int v, const float* k1, const int k1d[3], const float* 
 }
 
 std::vector<float> Engine::conv_same(const std::vector<float>& in, const int d[3], const std::vector<float>& k, const int kd[3]) {
+    // zero-extended "same"-size convolution of two PSF-sized volumes (DeconViewPSF.java:152-178,215-225); the tile plan is cached
+    // because every call of one derivation has the same extents
     std::vector<float> out(in.size());
-    convolve_host(cfg_.device, stream_, tables_.get(), cfg_.max_len, in.data(), d, k.data(), kd, EXT_ZERO, 0.f, out.data(), false);
+    bool same = small_conv_ != nullptr;
+    for (int a = 0; a < 3; ++a) same = same && small_dims_[a] == d[a] && small_kd_[a] == kd[a];
+    if (!same) {
+        Geometry g;
+        Reach r1[3], r2[3];
+        for (int a = 0; a < 3; ++a) {
+            g.gdim[a] = g.vol[a] = d[a]; g.goff[a] = 0; g.own_lo[a] = 0; g.own_hi[a] = d[a];
+            r1[a] = reach_of(kd[a]); r2[a] = Reach{0, 0};
+            small_dims_[a] = d[a]; small_kd_[a] = kd[a];
+        }
+        small_conv_.reset(new Convolver(g, r1, r2, 0, cfg_.max_len, stream_, tables_.get()));
+    }
+    const size_t n = in.size();
+    float* s = (float*)dev::alloc(sizeof(float) * n * 2);
+    cpx* khat = nullptr;
+    try {
+        dev::h2d(s, in.data(), sizeof(float) * n, stream_);
+        khat = small_conv_->build_khat(k.data(), kd);
+        small_conv_->conv(s, s + n, khat, EXT_ZERO, 0.f);
+        dev::d2h(out.data(), s + n, sizeof(float) * n, stream_);
+        dev::sync(stream_);
+    } catch (...) { dev::free_(s); dev::free_(khat); throw; }
+    dev::free_(s); dev::free_(khat);
     return out;
 }
 
@@ -612,6 +657,7 @@ void Engine::psi_init(int type, double sigma, double* avg_out, float* max_out) {
     ViewPtrs vp;
     for (int j = 0; j < V; ++j) {
         if (!views_[j].img) throw Error("view without image");
+        if (views_[j].pending) { dev::stream_wait(stream_, views_[j].ready); views_[j].pending = false; }
         vp.img[j] = views_[j].img;
         vp.weight[j] = views_[j].weight;
     }
@@ -738,6 +784,7 @@ void Engine::iteration_mul() {
     for (int v = 0; v < V; ++v) {                            // all views from the SAME psi
         View& vw = views_[v];
         if (!vw.img || !vw.weight) throw Error("view without image/weight");
+        if (vw.pending) { dev::stream_wait(stream_, vw.ready); vw.pending = false; }
         conv_->integral(psi_[cur_], vw.img, vw.k1hat, vw.k2hat, integral_[v]);
         mp.integral[v] = integral_[v];
         mp.weight[v] = vw.weight;
@@ -757,6 +804,7 @@ void Engine::view_update(int v) {
     dev::set_device(cfg_.device);
     View& vw = views_[v];
     if (!vw.img || !vw.weight) throw Error("view without image/weight");
+    if (vw.pending) { dev::stream_wait(stream_, vw.ready); vw.pending = false; }
     ensure_stats_slot();
     const int nparts = conv_->num_tiles() * conv_->parts_per_tile();
     conv_->view_update(psi_[cur_], psi_[cur_ ^ 1], vw.img, vw.weight, vw.k1hat, vw.k2hat, cfg_.lambda, cfg_.min_value,

@@ -174,6 +174,9 @@ class Engine {
     const Config& config() const { return cfg_; }
 
     void set_view_host(int v, const float* img, const float* weight);
+    // asynchronous upload on a copy stream (host buffers should be pinned and must stay valid until the next synchronisation); the
+    // first view update of view v waits for its upload only, so the uploads of later views overlap the first iteration
+    void set_view_host_async(int v, const float* img, const float* weight);
     void set_view_device(int v, const float* img, const float* weight);
     void set_psf(int v, const float* psf, const int kd[3]);
     void set_kernels(int v, const float* k1, const int k1d[3], const float* k2, const int k2d[3]);
@@ -223,7 +226,12 @@ class Engine {
         cpx* k1hat = nullptr;
         cpx* k2hat = nullptr;
         float max_intensity = 1.f;
+        dev::event_t ready = nullptr;   // upload finished (async uploads)
+        bool pending = false;
     };
+    stream_t copy_stream_ = nullptr;
+    std::unique_ptr<Convolver> small_conv_;   // cached plan of the PSF-derivation convolutions
+    int small_dims_[3] = {0, 0, 0}, small_kd_[3] = {0, 0, 0};
     void derive_kernels();
     std::vector<float> conv_same(const std::vector<float>& in, const int d[3], const std::vector<float>& k, const int kd[3]);
 

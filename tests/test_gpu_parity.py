@@ -367,3 +367,19 @@ def test_c4_like_independent_eight_views_device_weights(product_lib, oracle):
         assert oracle.rel_l2(dec.getPSI(), ref) <= 3 * rel_tol(2)       # psi0 differs at 1e-7 (FFT Gaussian vs separable sum)
     finally:
         dv.close()
+
+
+def test_async_upload_equals_synchronous(product_lib, oracle, small_dataset):
+    import mvrecon_b200 as m
+    views, psi0, avg = oracle.make_oracle_views(small_dataset, oracle.EFFICIENT_BAYESIAN)
+    outs = []
+    for asyn in (False, True):
+        dv = m.DeconViews(_views(m, small_dataset, 2), lambda_=0.006, async_upload=asyn)
+        try:
+            dec = m.MultiViewDeconvolutionSeq(dv, 2, m.PsiInitFromRAI(psi0, [v.max_intensity for v in views]))
+            dec.runIterations()
+            buf = np.empty_like(psi0)
+            outs.append(dec.getPSI(out=buf).copy())
+        finally:
+            dv.close()
+    assert np.array_equal(outs[0], outs[1])
