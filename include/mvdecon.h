@@ -135,6 +135,12 @@ MVD_API int mvd_psi_init(mvd_context* ctx, int type, double sigma, double* avg_o
  * mvd_normalize_weights: NormalizingRandomAccess over all views in place (normalization/NormalizingRandomAccess.java:75-109,183-214);
  * reference defaults: osem_speedup 1, additional_smooth 0, max_diff_range 0.1, scaling_range 0.05.  mvd_get_weight: download.        */
 MVD_API int mvd_make_blending_weights(mvd_context* ctx, int v, const int box_min[3], const int box_max[3], const float border[3], const float blending[3]);
+/* Same for a view whose image interval [img_min, img_max] lives in its own (rotated / scaled) coordinate system:
+ * TransformWeight.transformBlending (M/process/fusion/transformed/TransformWeight.java:82-139): every fused voxel (+ bbox_offset, the
+ * bounding-box min) is mapped through inv_affine -- the row-packed 3x4 INVERSE of the view -> fused-space AffineTransform3D -- in double,
+ * cast to float (TransformedRasteredRandomAccess.applyInverse, .../weights/TransformedRasteredRandomAccess.java:96-114), then weighted.  */
+MVD_API int mvd_make_blending_weights_affine(mvd_context* ctx, int v, const int img_min[3], const int img_max[3], const float border[3],
+                                             const float blending[3], const double inv_affine[12], const int bbox_offset[3]);
 MVD_API int mvd_normalize_weights(mvd_context* ctx, double osem_speedup, int additional_smooth, float max_diff_range, float scaling_range);
 MVD_API int mvd_get_weight(mvd_context* ctx, int v, float* weight_host);
 

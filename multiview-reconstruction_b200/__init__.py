@@ -87,6 +87,7 @@ SYMBOLS = {
     "mvd_set_max_intensities": (C.c_int, [C.c_void_p, _F]),
     "mvd_psi_init": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _D, _F]),
     "mvd_make_blending_weights": (C.c_int, [C.c_void_p, C.c_int, _I, _I, _F, _F]),
+    "mvd_make_blending_weights_affine": (C.c_int, [C.c_void_p, C.c_int, _I, _I, _F, _F, _D, _I]),
     "mvd_normalize_weights": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_float, C.c_float]),
     "mvd_get_weight": (C.c_int, [C.c_void_p, C.c_int, _F]),
     "mvd_run_iteration_mul": (C.c_int, [C.c_void_p, _D]),
@@ -379,6 +380,14 @@ class DeconViews:
         b = (C.c_float * 3)(*[float(x) for x in border])
         r = (C.c_float * 3)(*[float(x) for x in blending])
         self.lib.check(self.lib.dll.mvd_make_blending_weights(self._ctx, int(v), _i3(box_min_xyz), _i3(box_max_xyz), b, r))
+
+    def makeBlendingWeightsAffine(self, v: int, img_min_xyz, img_max_xyz, inverse_affine_row_packed, bbox_offset_xyz=(0, 0, 0),
+                                  border=(0.0, 0.0, 0.0), blending=(12.0, 12.0, 12.0)):
+        """TransformWeight.transformBlending: blending of the view's image interval seen through the inverse affine transform."""
+        b = (C.c_float * 3)(*[float(x) for x in border])
+        r = (C.c_float * 3)(*[float(x) for x in blending])
+        im = (C.c_double * 12)(*[float(x) for x in np.asarray(inverse_affine_row_packed, dtype=np.float64).ravel()[:12]])
+        self.lib.check(self.lib.dll.mvd_make_blending_weights_affine(self._ctx, int(v), _i3(img_min_xyz), _i3(img_max_xyz), b, r, im, _i3(bbox_offset_xyz)))
 
     def normalizeWeights(self, osemspeedup: float = 1.0, additionalSmoothBlending: bool = False, maxDiffRange: float = 0.1, scalingRange: float = 0.05):
         self.lib.check(self.lib.dll.mvd_normalize_weights(self._ctx, float(osemspeedup), 1 if additionalSmoothBlending else 0,

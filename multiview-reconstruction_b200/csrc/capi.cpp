@@ -145,6 +145,14 @@ int mvd_make_blending_weights(mvd_context* ctx, int v, const int box_min[3], con
         ctx->engine->make_blending_weights(v, box_min, box_max, border, blending);
     });
 }
+int mvd_make_blending_weights_affine(mvd_context* ctx, int v, const int img_min[3], const int img_max[3], const float border[3],
+                                     const float blending[3], const double inv_affine[12], const int bbox_offset[3]) {
+    return guarded([&] {
+        require(ctx && img_min && img_max && border && blending && inv_affine && bbox_offset, "null argument");
+        for (int d = 0; d < 3; ++d) require(blending[d] > 0.f, "blending range must be positive");
+        ctx->engine->make_blending_weights(v, img_min, img_max, border, blending, inv_affine, bbox_offset);
+    });
+}
 int mvd_normalize_weights(mvd_context* ctx, double osem_speedup, int additional_smooth, float max_diff_range, float scaling_range) {
     return guarded([&] { require(ctx, "null context"); ctx->engine->normalize_view_weights(osem_speedup, additional_smooth != 0, max_diff_range, scaling_range); });
 }

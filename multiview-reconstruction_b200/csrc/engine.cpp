@@ -728,7 +728,8 @@ void Engine::psi_init(int type, double sigma, double* avg_out, float* max_out) {
     if (max_out) for (int j = 0; j < V; ++j) max_out[j] = mx[j];
 }
 
-void Engine::make_blending_weights(int v, const int box_min[3], const int box_max[3], const float border[3], const float blending[3]) {
+void Engine::make_blending_weights(int v, const int box_min[3], const int box_max[3], const float border[3], const float blending[3],
+                                   const double* inv_affine, const int* bbox_offset) {
     if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
     dev::set_device(cfg_.device);
     View& vw = views_[v];
@@ -741,7 +742,7 @@ void Engine::make_blending_weights(int v, const int box_min[3], const int box_ma
         dev::h2d(lut_dev_, lut.data(), sizeof(double) * lut.size(), stream_);
         dev::sync(stream_);
     }
-    blend_weights(stream_, vw.weight_owned, lut_dev_, cfg_.geom.vol, cfg_.geom.goff, box_min, box_max, border, blending);
+    blend_weights(stream_, vw.weight_owned, lut_dev_, cfg_.geom.vol, cfg_.geom.goff, box_min, box_max, border, blending, inv_affine, bbox_offset);
 }
 
 void Engine::normalize_view_weights(double osem_speedup, bool additional_smooth, float max_diff_range, float scaling_range) {

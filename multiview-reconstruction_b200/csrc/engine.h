@@ -146,7 +146,7 @@ void psi_fused_stats(stream_t s, const ViewPtrs& vp, int V, float* psi, long lon
 void fill_volume(stream_t s, float* p, long long n, float v);
 void slice_stats(stream_t s, const float* img, int nx, long long nyz, double* acc_dev, float* max_dev);
 void blend_weights(stream_t s, float* out, const double* lut_dev, const int vol[3], const int goff[3], const int box_min[3], const int box_max[3],
-                   const float border[3], const float blending[3]);
+                   const float border[3], const float blending[3], const double* inv_affine = nullptr, const int* bbox_offset = nullptr);
 std::vector<double> blend_lut();
 void normalize_weights(stream_t s, const WeightPtrs& w, int V, long long n, double osem, bool smooth, float max_diff_range, float scaling_range);
 void mul_combine(stream_t st, const MulPtrs& p, int V, const float* psi_in, float* psi_out, long long n, long long own0, long long own1, float lambda,
@@ -194,7 +194,8 @@ class Engine {
     // PsiInit on the device (PsiInitBlurredFused / PsiInitAvgPrecise / PsiInitAvgApprox): sets psi and the per-view maxima
     void psi_init(int type, double sigma, double* avg_out, float* max_out);
     // weight masks on the device: cosine blending of a view's box, then NormalizingRandomAccess over all views
-    void make_blending_weights(int v, const int box_min[3], const int box_max[3], const float border[3], const float blending[3]);
+    void make_blending_weights(int v, const int box_min[3], const int box_max[3], const float border[3], const float blending[3],
+                               const double* inv_affine = nullptr, const int* bbox_offset = nullptr);
     void normalize_view_weights(double osem_speedup, bool additional_smooth, float max_diff_range, float scaling_range);
     void get_weight_host(int v, float* out);
     // MultiViewDeconvolutionMul.runNextIteration: one psi update from all views (geometric mean of the integrals)

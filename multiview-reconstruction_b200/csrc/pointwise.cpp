@@ -146,14 +146,30 @@ void slice_stats(stream_t s, const float* img, int nx, long long nyz, double* ac
 // BlendingRealRandomAccess.computeWeight (M/process/fusion/transformed/weights/BlendingRealRandomAccess.java:95-130) for an
 // axis-aligned box on the integer grid; lut = the 1001-entry cosine table built exactly like the reference's static initialiser.
 // ---------------------------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+MVD_HD double d_mul(double a, double b) { return __dmul_rn(a, b); }
+MVD_HD double d_add(double a, double b) { return __dadd_rn(a, b); }
+#else
+MVD_HD double d_mul(double a, double b) { volatile double r = a * b; return r; }
+MVD_HD double d_add(double a, double b) { volatile double r = a + b; return r; }
+#endif
+
 struct BlendKernel {
     float* out; const double* lut;
     int nx, ny; int goff[3];
     int mn[3], dim_minus1[3];
     float border[3], blending[3];
+    int affine;            // 1: location = inverse affine of (voxel + offset)  (TransformedRasteredRandomAccess.applyInverse, :96-114)
+    double im[12];         // row-packed inverse of the view -> fused-space transform
+    int offset[3];         // bounding-box min (the fused volume is zero-min)
     MVD_HD void operator()(long long i) const {
         const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((long long)nx * ny));
-        const float loc[3] = {(float)(x + goff[0]), (float)(y + goff[1]), (float)(z + goff[2])};
+        float loc[3] = {(float)(x + goff[0]), (float)(y + goff[1]), (float)(z + goff[2])};
+        if (affine) {
+            const double t0 = (double)(x + goff[0] + offset[0]), t1 = (double)(y + goff[1] + offset[1]), t2 = (double)(z + goff[2] + offset[2]);
+            for (int r = 0; r < 3; ++r)      // s = t0*i0 + t1*i1 + t2*i2 + i3, evaluated left to right in double without contraction
+                loc[r] = (float)d_add(d_add(d_add(d_mul(t0, im[4 * r]), d_mul(t1, im[4 * r + 1])), d_mul(t2, im[4 * r + 2])), im[4 * r + 3]);
+        }
         float tmp[3];
         for (int d = 0; d < 3; ++d) {
             const float l = f_sub(loc[d], (float)mn[d]);
@@ -171,10 +187,13 @@ struct BlendKernel {
     }
 };
 void blend_weights(stream_t s, float* out, const double* lut_dev, const int vol[3], const int goff[3], const int box_min[3], const int box_max[3],
-                   const float border[3], const float blending[3]) {
+                   const float border[3], const float blending[3], const double* inv_affine, const int* bbox_offset) {
     BlendKernel k;
     k.out = out; k.lut = lut_dev; k.nx = vol[0]; k.ny = vol[1];
+    k.affine = inv_affine ? 1 : 0;
+    for (int i = 0; i < 12; ++i) k.im[i] = inv_affine ? inv_affine[i] : 0.0;
     for (int d = 0; d < 3; ++d) {
+        k.offset[d] = bbox_offset ? bbox_offset[d] : 0;
         k.goff[d] = goff[d]; k.mn[d] = box_min[d]; k.dim_minus1[d] = box_max[d] - box_min[d];
         k.border[d] = border[d]; k.blending[d] = blending[d];
     }

@@ -640,6 +640,37 @@ def blending_weight(dims_zyx: Sequence[int], box_min_xyz: Sequence[int], box_max
     return w
 
 
+def blending_weight_affine(dims_zyx: Sequence[int], bbox_offset_xyz: Sequence[int], inv_affine_row_packed: Sequence[float],
+                           img_min_xyz: Sequence[int], img_max_xyz: Sequence[int], border: Sequence[float], blending: Sequence[float]) -> np.ndarray:
+    """TransformWeight.transformBlending (M/process/fusion/transformed/TransformWeight.java:82-139): for every voxel of the zero-min fused
+    volume, (voxel + offset) goes through the inverse affine in double, evaluated left to right (TransformedRasteredRandomAccess.applyInverse,
+    M/process/fusion/transformed/weights/TransformedRasteredRandomAccess.java:96-114), is cast to float and weighted by
+    BlendingRealRandomAccess.computeWeight (:95-130) of the view's image interval."""
+    f32 = np.float32
+    nz, ny, nx = dims_zyx
+    im = np.asarray(inv_affine_row_packed, dtype=np.float64).ravel()
+    t2, t1, t0 = np.meshgrid(np.arange(nz, dtype=np.float64) + bbox_offset_xyz[2], np.arange(ny, dtype=np.float64) + bbox_offset_xyz[1],
+                             np.arange(nx, dtype=np.float64) + bbox_offset_xyz[0], indexing="ij")
+    loc = [(((t0 * im[4 * r] + t1 * im[4 * r + 1]) + t2 * im[4 * r + 2]) + im[4 * r + 3]).astype(f32) for r in range(3)]
+    w = np.ones((nz, ny, nx), dtype=f32)
+    zero = np.zeros((nz, ny, nx), dtype=bool)
+    facs = []
+    for d in range(3):
+        mn = int(img_min_xyz[d])
+        dim_minus1 = int(img_max_xyz[d]) - mn
+        l = (loc[d] - f32(mn)).astype(f32)
+        dist = np.minimum((l - f32(border[d])).astype(f32), ((f32(dim_minus1) - l).astype(f32) - f32(border[d])).astype(f32))
+        zero |= dist <= 0
+        rel = (dist / f32(blending[d])).astype(f32)
+        with np.errstate(invalid="ignore"):
+            idx = np.clip((rel.astype(np.float64) * 1000.0 + 0.5).astype(np.int64), 0, 1000)
+        facs.append(np.where(rel < 1, _BLEND_LUT[idx], 1.0))
+    for fac in facs:                       # minDistance (float) *= lookUp (double), dimension order x, y, z
+        w = (w.astype(np.float64) * fac).astype(f32)
+    w[zero] = 0
+    return w
+
+
 def smooth_weights(w: np.ndarray, sumw: np.ndarray, max_diff_range=MAX_DIFF_RANGE, scaling_range=SCALING_RANGE) -> np.ndarray:
     """NormalizingRandomAccess.smoothWeights (NormalizingRandomAccess.java:183-201)."""
     f32 = np.float32

@@ -98,3 +98,28 @@ def check_mul_iteration_matches_oracle(lib, oracle, small_dataset, lam):
             assert abs(st.sumChange - s) <= 2e-4 * abs(s) + 0.5 and abs(st.maxChange - mx) <= 2e-3 * abs(mx) + 1e-3
     finally:
         dv.close()
+
+
+def check_affine_blending_weights(lib, oracle):
+    """rotated + scaled view box: device weights == oracle restatement of TransformWeight.transformBlending, bit for bit"""
+    import mvrecon_b200 as m
+    dims = (30, 36, 44)
+    th = np.deg2rad(27.0)
+    fwd = np.array([[np.cos(th), 0.0, np.sin(th) * 1.7, 9.3], [0.0, 1.0, 0.0, -2.25], [-np.sin(th), 0.0, np.cos(th) * 1.7, 14.1], [0, 0, 0, 1.0]])
+    inv = np.linalg.inv(fwd)[:3].ravel()
+    img_min, img_max, off = (0, 0, 0), (39, 35, 19), (-3, 1, 2)
+    ref = oracle.blending_weight_affine(dims, off, inv, img_min, img_max, (2.0, 1.0, 0.5), (12.0, 10.0, 6.0))
+    assert 0 < np.count_nonzero(ref) < ref.size and ref.max() == 1.0
+    img = np.ones(dims, np.float32)
+    dv = m.DeconViews([m.DeconView(img, None, np.ones((3, 3, 3), np.float32))], library=lib)
+    try:
+        dv.makeBlendingWeightsAffine(0, img_min, img_max, inv, off, (2.0, 1.0, 0.5), (12.0, 10.0, 6.0))
+        got = dv.getWeight(0)
+    finally:
+        dv.close()
+    assert np.array_equal(got, ref)
+    # identity transform reduces to the axis-aligned case
+    ident = np.eye(4)[:3].ravel()
+    a = oracle.blending_weight_affine(dims, (0, 0, 0), ident, (4, 3, 2), (40, 30, 25), (0, 0, 0), (12, 12, 12))
+    b = oracle.blending_weight(dims, (4, 3, 2), (40, 30, 25), (0, 0, 0), (12, 12, 12))
+    assert np.array_equal(a, b)

@@ -22,3 +22,7 @@ def test_psi_init_variants(product_lib, oracle, small_dataset):
 @pytest.mark.parametrize("lam", [0.0, 0.006])
 def test_mul_iteration_matches_oracle(product_lib, oracle, small_dataset, lam):
     X.check_mul_iteration_matches_oracle(product_lib, oracle, small_dataset, lam)
+
+
+def test_affine_blending_weights(product_lib, oracle):
+    X.check_affine_blending_weights(product_lib, oracle)

@@ -20,3 +20,7 @@ def test_psi_init_variants(hostemu_lib, oracle, small_dataset):
 @pytest.mark.parametrize("lam", [0.0, 0.006])
 def test_mul_iteration_matches_oracle(hostemu_lib, oracle, small_dataset, lam):
     X.check_mul_iteration_matches_oracle(hostemu_lib, oracle, small_dataset, lam)
+
+
+def test_affine_blending_weights(hostemu_lib, oracle):
+    X.check_affine_blending_weights(hostemu_lib, oracle)
