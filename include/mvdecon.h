@@ -167,13 +167,17 @@ MVD_API int mvd_psi_device_ptr(mvd_context* ctx, void** current);           /* d
 MVD_API int mvd_stream_handle(mvd_context* ctx, void** cuda_stream);
 
 /* Multi-GPU: one process (or context) per GPU on a py x pz (y x z) grid of boxes, rank = ry * pz + rz (mvd_config.shard_* describe the
- * box).  mvd_comm_unique_id: rank 0 creates a 128-byte NCCL id that the host distributes with its own plumbing; mvd_comm_init
- * (after mvd_init_views, collective) attaches a communicator.  From then on every view update / Mul iteration is followed by the halo
- * exchange of the new psi (y rows first, then z planes including the fresh y halos), enqueued on the context's stream -- so
- * mvd_run_iterations works unchanged across GPUs.  mvd_exchange_halos triggers one exchange explicitly (e.g. after mvd_set_psi).
+ * box).  mvd_comm_unique_id: rank 0 creates a 128-byte NCCL id that the host distributes with its own plumbing.  mvd_comm_create
+ * (collective) builds a communicator for `device` once per process -- it is reusable across contexts and jobs -- and
+ * mvd_comm_attach (after mvd_init_views) attaches it to a context.  From then on every view update / Mul iteration is followed by the
+ * halo exchange of the new psi (y rows first, then z planes including the fresh y halos), enqueued on the context's stream -- so
+ * mvd_run_iterations works unchanged across GPUs.  mvd_exchange_halos triggers one exchange explicitly (e.g. after mvd_psi_init).
  * NCCL is loaded with dlopen on first use; single-GPU use needs no NCCL.                                                              */
+typedef struct mvd_comm mvd_comm;
 MVD_API int mvd_comm_unique_id(char id_out[128]);
-MVD_API int mvd_comm_init(mvd_context* ctx, const char id[128], int world, int rank, int py, int pz);
+MVD_API int mvd_comm_create(const char id[128], int world, int rank, int device, mvd_comm** out);
+MVD_API int mvd_comm_destroy(mvd_comm* comm);
+MVD_API int mvd_comm_attach(mvd_context* ctx, mvd_comm* comm, int py, int pz);
 MVD_API int mvd_exchange_halos(mvd_context* ctx);
 
 /* Per-pass device timing (CUDA events on the context's stream around every pass launch): slots 0..8 = passes P1..P9 of a

@@ -102,7 +102,9 @@ SYMBOLS = {
     "mvd_psi_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "mvd_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "mvd_comm_unique_id": (C.c_int, [C.c_char_p]),
-    "mvd_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mvd_comm_create": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "mvd_comm_destroy": (C.c_int, [C.c_void_p]),
+    "mvd_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mvd_exchange_halos": (C.c_int, [C.c_void_p]),
     "mvd_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "mvd_get_pass_times": (C.c_int, [C.c_void_p, _D, C.POINTER(C.c_longlong), C.c_int]),
@@ -164,6 +166,12 @@ class Lib:
         self.check(self.dll.mvd_comm_unique_id(buf))
         return buf.raw
 
+    def comm_create(self, unique_id: bytes, world: int, rank: int, device: int) -> "Communicator":
+        """collective: one NCCL communicator per process / device, reusable across contexts (attach with DeconViews.comm_attach)"""
+        h = C.c_void_p()
+        self.check(self.dll.mvd_comm_create(C.create_string_buffer(bytes(unique_id), 128), int(world), int(rank), int(device), C.byref(h)))
+        return Communicator(self, h)
+
     def getNumDevicesCUDA(self) -> int:
         return int(self.dll.getNumDevicesCUDA())
 
@@ -192,6 +200,16 @@ class Lib:
                                                 _i3(_xyz(k1)), _fp(k2), _i3(_xyz(k2)), C.c_float(lambda_), C.c_float(min_value),
                                                 C.c_float(max_intensity), st))
         return float(st[0]), float(st[1])
+
+
+class Communicator:
+    def __init__(self, lib_: Lib, handle):
+        self.lib, self.handle = lib_, handle
+
+    def close(self):
+        if self.handle:
+            self.lib.dll.mvd_comm_destroy(self.handle)
+            self.handle = None
 
 
 _LIB: Optional[Lib] = None
@@ -408,9 +426,10 @@ class DeconViews:
         self.lib.check(self.lib.dll.mvd_stream_handle(self._ctx, C.byref(p)))
         return int(p.value or 0)
 
-    def comm_init(self, unique_id: bytes, world: int, rank: int, py: int, pz: int):
-        """attach the in-library NCCL halo exchange (collective over all ranks of the (y x z) grid, rank = ry * pz + rz)"""
-        self.lib.check(self.lib.dll.mvd_comm_init(self._ctx, C.create_string_buffer(bytes(unique_id), 128), int(world), int(rank), int(py), int(pz)))
+    def comm_attach(self, comm: "Communicator", py: int, pz: int):
+        """attach the in-library NCCL halo exchange for a py x pz (y x z) grid, rank = ry * pz + rz"""
+        self.lib.check(self.lib.dll.mvd_comm_attach(self._ctx, comm.handle, int(py), int(pz)))
+        self._comm = comm
 
     def exchange_halos(self):
         self.lib.check(self.lib.dll.mvd_exchange_halos(self._ctx))

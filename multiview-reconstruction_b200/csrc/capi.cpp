@@ -10,6 +10,7 @@
 
 using namespace mvd;
 
+struct mvd_comm { std::shared_ptr<NcclComm> comm; };
 struct mvd_context {
     Engine* engine = nullptr;
     int halo_lo = 0, halo_hi = 0;
@@ -234,10 +235,22 @@ int mvd_stream_handle(mvd_context* ctx, void** s) {
 }
 
 int mvd_comm_unique_id(char id_out[128]) {
-    return guarded([&] { require(id_out != nullptr, "null argument"); HaloComm::unique_id(id_out); });
+    return guarded([&] { require(id_out != nullptr, "null argument"); NcclComm::unique_id(id_out); });
 }
-int mvd_comm_init(mvd_context* ctx, const char id[128], int world, int rank, int py, int pz) {
-    return guarded([&] { require(ctx && id, "null argument"); ctx->engine->comm_init(id, world, rank, py, pz); });
+int mvd_comm_create(const char id[128], int world, int rank, int device, mvd_comm** out) {
+    return guarded([&] {
+        require(id && out, "null argument");
+        require_device(device);
+        mvd_comm* c = new mvd_comm();
+        try { c->comm = std::make_shared<NcclComm>(id, world, rank, device); } catch (...) { delete c; throw; }
+        *out = c;
+    });
+}
+int mvd_comm_destroy(mvd_comm* comm) {
+    return guarded([&] { delete comm; });
+}
+int mvd_comm_attach(mvd_context* ctx, mvd_comm* comm, int py, int pz) {
+    return guarded([&] { require(ctx && comm, "null argument"); ctx->engine->comm_attach(comm->comm, py, pz); });
 }
 int mvd_exchange_halos(mvd_context* ctx) {
     return guarded([&] { require(ctx, "null context"); ctx->engine->exchange_halos(); });

@@ -46,11 +46,6 @@ void nccl_check(ncclResult_t r, const char* what) {
 constexpr int kNcclFloat = 7;
 }  // namespace
 
-struct HaloComm::Impl {
-    ncclComm_t comm = nullptr;
-};
-#else
-struct HaloComm::Impl {};
 #endif
 
 // copy rows [ya, ya+rows) of planes [za, za+planes) between the local volume and a dense staging buffer
@@ -65,7 +60,7 @@ struct PackRows {
     }
 };
 
-void HaloComm::unique_id(char out[128]) {
+void NcclComm::unique_id(char out[128]) {
 #ifndef MVD_HOST_EMU
     ncclUniqueId id;
     nccl_check(nccl().GetUniqueId(&id), "ncclGetUniqueId");
@@ -76,30 +71,38 @@ void HaloComm::unique_id(char out[128]) {
 #endif
 }
 
-HaloComm::HaloComm(const char id[128], int world, int rank, int py, int pz, const Geometry& g, int halo_y, int halo_z, stream_t s)
-    : impl_(new Impl()), world_(world), rank_(rank), py_(py), pz_(pz), g_(g), hy_(halo_y), hz_(halo_z), stream_(s) {
-    if (py * pz != world || rank < 0 || rank >= world) throw Error("bad process grid");
-    ry_ = rank / pz; rz_ = rank % pz;
+NcclComm::NcclComm(const char id[128], int world, int rank, int device) : world_(world), rank_(rank), device_(device) {
+    if (world < 1 || rank < 0 || rank >= world) throw Error("bad communicator rank / size");
 #ifndef MVD_HOST_EMU
+    dev::set_device(device);
     ncclUniqueId uid;
     std::memcpy(uid.internal, id, 128);
-    nccl_check(nccl().CommInitRank(&impl_->comm, world, uid, rank), "ncclCommInitRank");
-    if (py > 1) {
-        const size_t n = (size_t)hy_ * g.vol[0] * (size_t)(g.own_hi[2] - g.own_lo[2]);
-        for (int i = 0; i < 4; ++i) stage_[i] = (float*)dev::alloc(sizeof(float) * n);
-    }
+    ncclComm_t c = nullptr;
+    nccl_check(nccl().CommInitRank(&c, world, uid, rank), "ncclCommInitRank");
+    comm_ = c;
 #else
     (void)id;
     throw Error("the host emulator has no NCCL");
 #endif
 }
+NcclComm::~NcclComm() {
+#ifndef MVD_HOST_EMU
+    if (comm_) nccl().CommDestroy((ncclComm_t)comm_);
+#endif
+}
+
+HaloComm::HaloComm(std::shared_ptr<NcclComm> comm, int py, int pz, const Geometry& g, int halo_y, int halo_z, stream_t s)
+    : comm_(std::move(comm)), py_(py), pz_(pz), g_(g), hy_(halo_y), hz_(halo_z), stream_(s) {
+    if (!comm_ || py * pz != comm_->world()) throw Error("bad process grid");
+    ry_ = comm_->rank() / pz; rz_ = comm_->rank() % pz;
+    if (py > 1) {
+        const size_t n = (size_t)hy_ * g.vol[0] * (size_t)(g.own_hi[2] - g.own_lo[2]);
+        for (int i = 0; i < 4; ++i) stage_[i] = (float*)dev::alloc(sizeof(float) * n);
+    }
+}
 
 HaloComm::~HaloComm() {
-#ifndef MVD_HOST_EMU
     for (float* p : stage_) dev::free_(p);
-    if (impl_ && impl_->comm) nccl().CommDestroy(impl_->comm);
-#endif
-    delete impl_;
 }
 
 void HaloComm::exchange(float* psi) {
@@ -116,12 +119,12 @@ void HaloComm::exchange(float* psi) {
         if (upper) pfor(cnt, PackRows{psi, stage_[1], nx, ny, yhi - hy_, zlo, hy_, 1}, stream_);
         nccl_check(n.GroupStart(), "group");
         if (lower) {
-            nccl_check(n.Send(stage_[0], (size_t)cnt, kNcclFloat, (ry_ - 1) * pz_ + rz_, impl_->comm, stream_), "send");
-            nccl_check(n.Recv(stage_[2], (size_t)cnt, kNcclFloat, (ry_ - 1) * pz_ + rz_, impl_->comm, stream_), "recv");
+            nccl_check(n.Send(stage_[0], (size_t)cnt, kNcclFloat, (ry_ - 1) * pz_ + rz_, (ncclComm_t)comm_->raw(), stream_), "send");
+            nccl_check(n.Recv(stage_[2], (size_t)cnt, kNcclFloat, (ry_ - 1) * pz_ + rz_, (ncclComm_t)comm_->raw(), stream_), "recv");
         }
         if (upper) {
-            nccl_check(n.Send(stage_[1], (size_t)cnt, kNcclFloat, (ry_ + 1) * pz_ + rz_, impl_->comm, stream_), "send");
-            nccl_check(n.Recv(stage_[3], (size_t)cnt, kNcclFloat, (ry_ + 1) * pz_ + rz_, impl_->comm, stream_), "recv");
+            nccl_check(n.Send(stage_[1], (size_t)cnt, kNcclFloat, (ry_ + 1) * pz_ + rz_, (ncclComm_t)comm_->raw(), stream_), "send");
+            nccl_check(n.Recv(stage_[3], (size_t)cnt, kNcclFloat, (ry_ + 1) * pz_ + rz_, (ncclComm_t)comm_->raw(), stream_), "recv");
         }
         nccl_check(n.GroupEnd(), "group");
         if (lower) pfor(cnt, PackRows{psi, stage_[2], nx, ny, ylo - hy_, zlo, hy_, 0}, stream_);
@@ -131,12 +134,12 @@ void HaloComm::exchange(float* psi) {
         const size_t plane = (size_t)nx * ny, cnt = plane * hz_;
         nccl_check(n.GroupStart(), "group");
         if (rz_ > 0) {
-            nccl_check(n.Send(psi + plane * zlo, cnt, kNcclFloat, ry_ * pz_ + rz_ - 1, impl_->comm, stream_), "send");
-            nccl_check(n.Recv(psi + plane * (zlo - hz_), cnt, kNcclFloat, ry_ * pz_ + rz_ - 1, impl_->comm, stream_), "recv");
+            nccl_check(n.Send(psi + plane * zlo, cnt, kNcclFloat, ry_ * pz_ + rz_ - 1, (ncclComm_t)comm_->raw(), stream_), "send");
+            nccl_check(n.Recv(psi + plane * (zlo - hz_), cnt, kNcclFloat, ry_ * pz_ + rz_ - 1, (ncclComm_t)comm_->raw(), stream_), "recv");
         }
         if (rz_ < pz_ - 1) {
-            nccl_check(n.Send(psi + plane * (zhi - hz_), cnt, kNcclFloat, ry_ * pz_ + rz_ + 1, impl_->comm, stream_), "send");
-            nccl_check(n.Recv(psi + plane * zhi, cnt, kNcclFloat, ry_ * pz_ + rz_ + 1, impl_->comm, stream_), "recv");
+            nccl_check(n.Send(psi + plane * (zhi - hz_), cnt, kNcclFloat, ry_ * pz_ + rz_ + 1, (ncclComm_t)comm_->raw(), stream_), "send");
+            nccl_check(n.Recv(psi + plane * zhi, cnt, kNcclFloat, ry_ * pz_ + rz_ + 1, (ncclComm_t)comm_->raw(), stream_), "recv");
         }
         nccl_check(n.GroupEnd(), "group");
     }

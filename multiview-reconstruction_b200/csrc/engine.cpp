@@ -820,17 +820,18 @@ void Engine::view_update(int v) {
     if (comm_) comm_->exchange(psi_[cur_]);
 }
 
-void Engine::comm_init(const char id[128], int world, int rank, int py, int pz) {
-    if (!inited_) throw Error("init_views() must run before comm_init (the halo widths come from the kernels)");
+void Engine::comm_attach(std::shared_ptr<NcclComm> comm, int py, int pz) {
+    if (!inited_) throw Error("init_views() must run before the communicator is attached (the halo widths come from the kernels)");
+    if (!comm || comm->device() != cfg_.device) throw Error("communicator belongs to another device");
     dev::set_device(cfg_.device);
     const Geometry& g = cfg_.geom;
     const bool ysh = g.own_lo[1] != 0 || g.own_hi[1] != g.gdim[1], zsh = g.own_lo[2] != 0 || g.own_hi[2] != g.gdim[2];
     if ((py > 1) != ysh || (pz > 1) != zsh) throw Error("process grid does not match the sharding of this context");
     const int hy = std::max(halo_y_lo_, halo_y_hi_), hz = std::max(halo_lo_, halo_hi_);
-    comm_.reset(new HaloComm(id, world, rank, py, pz, g, hy, hz, stream_));
+    comm_.reset(new HaloComm(std::move(comm), py, pz, g, hy, hz, stream_));
 }
 void Engine::exchange_halos() {
-    if (!comm_) throw Error("no communicator attached (mvd_comm_init)");
+    if (!comm_) throw Error("no communicator attached (mvd_comm_attach)");
     dev::set_device(cfg_.device);
     comm_->exchange(psi_[cur_]);
 }

@@ -121,16 +121,27 @@ void convolve_host(int device, stream_t s, Tables* tables, int max_len, const fl
 struct IterStats { double sum_change; double max_change; };
 
 // in-library halo exchange over NCCL for a (y x z) process grid (comm.cpp)
-class HaloComm {
+class NcclComm {                         // one communicator per process and device; reusable across contexts / jobs
   public:
     static void unique_id(char out[128]);
-    HaloComm(const char id[128], int world, int rank, int py, int pz, const Geometry& g, int halo_y, int halo_z, stream_t s);
+    NcclComm(const char id[128], int world, int rank, int device);
+    ~NcclComm();
+    int world() const { return world_; }
+    int rank() const { return rank_; }
+    int device() const { return device_; }
+    void* raw() const { return comm_; }
+  private:
+    void* comm_ = nullptr;
+    int world_, rank_, device_;
+};
+class HaloComm {
+  public:
+    HaloComm(std::shared_ptr<NcclComm> comm, int py, int pz, const Geometry& g, int halo_y, int halo_z, stream_t s);
     ~HaloComm();
     void exchange(float* psi);          // enqueued on the stream; the host does not block
   private:
-    struct Impl;
-    Impl* impl_;
-    int world_, rank_, py_, pz_, ry_ = 0, rz_ = 0;
+    std::shared_ptr<NcclComm> comm_;
+    int py_, pz_, ry_ = 0, rz_ = 0;
     Geometry g_;
     int hy_, hz_;
     stream_t stream_;
@@ -201,7 +212,7 @@ class Engine {
     // MultiViewDeconvolutionMul.runNextIteration: one psi update from all views (geometric mean of the integrals)
     void iteration_mul();
     // attach the NCCL halo exchange: afterwards every view update / Mul iteration is followed by the exchange of the new psi
-    void comm_init(const char id[128], int world, int rank, int py, int pz);
+    void comm_attach(std::shared_ptr<NcclComm> comm, int py, int pz);
     void exchange_halos();
     void view_update(int v);                               // asynchronous on the engine stream
     void fetch_stats(int count, IterStats* out);           // last `count` view updates (synchronises)

@@ -1,6 +1,8 @@
 // Instantiates the seven pass kernels for one FFT length and exposes them as a LenOps record.
 // Included by the generated per-length translation units (gen/len_<N>.cu) so that lengths compile in parallel.
 #pragma once
+#include <atomic>
+
 #include "backend.h"
 
 namespace mvd {
@@ -38,6 +40,17 @@ __global__ void __launch_bounds__(P::XTHREADS, x_min_blocks<P>()) x_kernel(const
 }
 #endif
 
+#ifndef MVD_HOST_EMU
+// cudaFuncSetAttribute is a per-device setting: remember which devices of this process already have it (the reference drives several
+// devices from one process, one Java thread each -- MultiViewDeconvolutionSeq.java:92-150)
+inline bool first_use_on_current_device(std::atomic<unsigned long long>& mask) {
+    int d = 0;
+    MVD_CUDA_CHECK(cudaGetDevice(&d));
+    const unsigned long long bit = 1ull << (d & 63);
+    return (mask.fetch_or(bit) & bit) == 0;
+}
+#endif
+
 inline int carveout_pref() {   // MVD_CARVEOUT: -1 = driver default, 0..100 = preferred shared-memory carveout in percent
     static const int v = [] { const char* e = std::getenv("MVD_CARVEOUT"); return e ? std::atoi(e) : -1; }();
     return v;
@@ -61,11 +74,10 @@ struct LenImpl {
         for (int by = 0; by < gy; ++by)
             for (int bx = 0; bx < gx; ++bx) col_pass_body<P, MODE>(ex, a, bx, by, sm.data());
 #else
-        static bool attr_done = false;
-        if (!attr_done) {
+        static std::atomic<unsigned long long> attr_mask{0};
+        if (first_use_on_current_device(attr_mask)) {
             MVD_CUDA_CHECK(cudaFuncSetAttribute(col_kernel<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
             if (carveout_pref() >= 0) MVD_CUDA_CHECK(cudaFuncSetAttribute(col_kernel<P, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pref()));
-            attr_done = true;
         }
         col_kernel<P, MODE><<<dim3(gx, gy), P::THREADS, smem_col, s>>>(a);
         MVD_CUDA_CHECK(cudaGetLastError());
@@ -81,11 +93,10 @@ struct LenImpl {
         HostExec ex(PX::XTHREADS);
         for (int bx = 0; bx < nblocks; ++bx) x_pass_body<PX, KIND>(ex, a, bx, sm, li);
 #else
-        static bool attr_done = false;
-        if (!attr_done) {
+        static std::atomic<unsigned long long> attr_mask{0};
+        if (first_use_on_current_device(attr_mask)) {
             MVD_CUDA_CHECK(cudaFuncSetAttribute(x_kernel<PX, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
             if (carveout_pref() >= 0) MVD_CUDA_CHECK(cudaFuncSetAttribute(x_kernel<PX, KIND>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pref()));
-            attr_done = true;
         }
         x_kernel<PX, KIND><<<nblocks, PX::XTHREADS, smem_x, s>>>(a);
         MVD_CUDA_CHECK(cudaGetLastError());

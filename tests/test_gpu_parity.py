@@ -383,3 +383,81 @@ def test_async_upload_equals_synchronous(product_lib, oracle, small_dataset):
         finally:
             dv.close()
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_two_devices_in_one_process(product_lib, oracle):
+    """the reference's multi-GPU model: one process, one worker per device (ComputeBlockSeqThreadCUDAFactory.java:57-64)"""
+    if product_lib.getNumDevicesCUDA() < 2:
+        pytest.skip("needs two devices")
+    import threading
+    rng = np.random.default_rng(9)
+    img = rng.random((64, 48, 80)).astype(np.float32)
+    k = rng.random((9, 7, 5)).astype(np.float32)
+    ref = oracle.fft_convolve(img, k, "mirror", dtype=np.float64)
+    out = {}
+
+    def work(dev):
+        out[dev] = product_lib.convolve(img, k, "mirror", device=dev)
+
+    ts = [threading.Thread(target=work, args=(d,)) for d in (0, 1)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for d in (0, 1):
+        assert oracle.rel_l2(out[d], ref) < 5e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("axis", ["z", "y"])
+def test_in_library_halo_exchange_two_gpus(product_lib, oracle, axis):
+    """two contexts on two devices joined by the library's own NCCL exchange (mvd_comm_create / mvd_comm_attach): mvd_run_iterations
+    on each shard, without any host-side exchange, must equal the whole-volume update"""
+    if product_lib.getNumDevicesCUDA() < 2:
+        pytest.skip("needs two devices")
+    import threading
+    import mvrecon_b200 as m
+    ds = oracle.make_synthetic((48, 40, 36), 2, seed=5, psf_size_xyz=(5, 7, 5), psf_sigma_xyz=(1.0, 1.4, 1.2), bead_density=1024)
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN)
+    mx = [v.max_intensity for v in views]
+    nz, ny = 48, 40
+    n = nz if axis == "z" else ny
+    cut, H = n // 2 + 3, 8
+    uid = product_lib.comm_unique_id()
+    res, err = {}, []
+
+    def work(r):
+        try:
+            lo, hi = (0, cut) if r == 0 else (cut, n)
+            a0, a1 = max(0, lo - H), min(n, hi + H)
+            sl = (slice(a0, a1),) if axis == "z" else (slice(None), slice(a0, a1))
+            loc = [m.DeconView(np.ascontiguousarray(ds.images[v][sl]), np.ascontiguousarray(ds.weights[v][sl]), ds.psfs[v],
+                               m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(2)]
+            kw = {"shard": (lo, hi, a0, a1 - a0)} if axis == "z" else {"shard_y": (lo, hi, a0, a1 - a0)}
+            d = m.DeconViews(loc, global_dims_zyx=(nz, ny, 36), device=r, **kw)
+            comm = product_lib.comm_create(uid, 2, r, r)
+            d.comm_attach(comm, *((1, 2) if axis == "z" else (2, 1)))
+            dec = m.MultiViewDeconvolutionSeq(d, 2, m.PsiInitFromRAI(np.ascontiguousarray(psi0[sl]), mx))
+            dec.runIterations()
+            own = (slice(lo - a0, hi - a0),) if axis == "z" else (slice(None), slice(lo - a0, hi - a0))
+            res[r] = (lo, hi, dec.getPSI()[own].copy())
+            d.close()
+            comm.close()
+        except Exception as e:  # noqa: BLE001
+            err.append(e)
+
+    ts = [threading.Thread(target=work, args=(r,), daemon=True) for r in (0, 1)]
+    [t.start() for t in ts]
+    [t.join(timeout=120) for t in ts]
+    assert not err, err
+    assert len(res) == 2
+    psi64 = psi0
+    for it in range(2):
+        for v in range(2):
+            psi64, _, _ = oracle.view_update_whole(psi64, views[v], 0.0, dtype=np.float64)
+    full = np.empty_like(psi0)
+    for r in (0, 1):
+        lo, hi, part = res[r]
+        if axis == "z":
+            full[lo:hi] = part
+        else:
+            full[:, lo:hi] = part
+    assert oracle.rel_l2(full, psi64) <= rel_tol(2)
