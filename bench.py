@@ -300,8 +300,14 @@ def run_ours(args):
     dims, V, psf_xyz, sigma, lam, ptype = WORKLOADS[name]
     nz, ny, nx = dims
     from mvrecon_b200 import sharding
-    Hy, Hz = psf_xyz[1] - 1, psf_xyz[2] - 1                  # psi halo per interior side = k1/2 + k2/2 along that axis
-    py, pz = sharding.grid_for(world, ny, nz, (psf_xyz[1] - 1) // 2, (psf_xyz[2] - 1) // 2, lib.supported_fft_lengths())
+    use_lib_comm = world > 1 and os.environ.get("BENCH_EXCHANGE", "lib") == "lib"
+    # exchange scheme 1 (psi by k1/2, then the quotient by k2/2; interior halo max(k1/2, k2/2)) needs the in-library exchange;
+    # scheme 0 ships k1/2 + k2/2 of psi only.  BENCH_SCHEME=0 selects the single-exchange scheme for comparison.
+    scheme = int(os.environ.get("BENCH_SCHEME", "1")) if use_lib_comm else 0
+    Hy, Hz = ((psf_xyz[1] - 1) // 2, (psf_xyz[2] - 1) // 2) if scheme == 1 else (psf_xyz[1] - 1, psf_xyz[2] - 1)
+    py, pz = sharding.grid_for(world, ny, nz, (psf_xyz[1] - 1) // 2, (psf_xyz[2] - 1) // 2, lib.supported_fft_lengths(), scheme)
+    if os.environ.get("BENCH_GRID"):                         # experiments: "PYxPZ"
+        py, pz = (int(x) for x in os.environ["BENCH_GRID"].split("x"))
     ry, rz = rank // pz, rank % pz
     rank_of = lambda a, b: a * pz + b
     ylo, yhi = sharding.slab_range(ny, py, ry)
@@ -319,7 +325,8 @@ def run_ours(args):
 
     def build(views_data, async_upload=False):
         views = [m.DeconView(im, w, psfs[v], m.PSFTYPE(ptype)) for v, (im, w) in enumerate(views_data)]
-        return m.DeconViews(views, device=local, lambda_=lam, shard=shard, shard_y=shard_y, global_dims_zyx=dims, async_upload=async_upload)
+        return m.DeconViews(views, device=local, lambda_=lam, shard=shard, shard_y=shard_y, global_dims_zyx=dims, async_upload=async_upload,
+                            exchange_scheme=scheme)
 
     # ---------------- kernel-only leg: everything resident --------------------------------------------------------
     dv = build([(m.DeviceArray.from_torch(im), m.DeviceArray.from_torch(w)) for im, w in zip(imgs, weights)])
@@ -337,8 +344,6 @@ def run_ours(args):
         with torch.cuda.stream(stream):
             buf = torch.as_tensor(m.RawDeviceBuffer(dv.psi_device_ptr(), (z1 - z0, y1 - y0, nx)), device=f"cuda:{local}")
             sharding.exchange_halos_2d(buf, (ylo, yhi), (y0, y1 - y0), (lo, hi), (z0, z1 - z0), Hy, Hz, ry, rz, py, pz, rank_of, dist)
-
-    use_lib_comm = world > 1 and os.environ.get("BENCH_EXCHANGE", "lib") == "lib"
 
     comm = None
     if use_lib_comm:                                         # one NCCL communicator per process, reused by every context of this run
@@ -464,7 +469,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[name], "step": f"one OSEM iteration = {V} view updates over the whole volume",
                        "fft_tile_xyz": info["tile_dims_xyz"], "tiles_per_gpu": info["num_tiles"], "fft_box_over_useful_voxels": round(info["fft_volume_ratio"], 4),
-                       "sharding": "none" if world == 1 else f"{py} x {pz} (y x z) boxes, psi halo exchange ({Hy} rows / {Hz} planes) per view update, NCCL send/recv enqueued on the compute stream " + ("by the library" if use_lib_comm else "by torch.distributed"),
+                       "sharding": "none" if world == 1 else f"{py} x {pz} (y x z) boxes, exchange scheme {scheme} (" + ("psi by k1/2 before + quotient spectrum by k2/2 inside" if scheme == 1 else "psi by k1/2 + k2/2 after") + f" every view update; local halo {Hy} rows / {Hz} planes), NCCL send/recv enqueued on the compute stream " + ("by the library" if use_lib_comm else "by torch.distributed"),
                        "l2_flush": "not needed: every pass streams >= 1.2 GB (inputs larger than the 126 MB L2)",
                        "roofline_fraction_92B": value * B_ALG / (peak * 1e9 * world), "output_finite": finite},
             "roofline": {"bound": "hbm", "kernel": PASS_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

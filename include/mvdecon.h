@@ -86,6 +86,12 @@ typedef struct mvd_config {
      * redundant halo volume small: the single-GPU plan already splits y into two FFT tiles, so a 2-way y split costs nothing.            */
     int shard_y_lo, shard_y_hi;
     int local_y0, local_ny;
+    /* Halo exchange scheme of a sharded context.  0 (A): one exchange of psi per view update; interior sides carry the reach of BOTH
+     * chained convolutions (k1/2 + k2/2) and the box recomputes the neighbour's quotient there.  1 (B): two exchanges -- psi by the
+     * reach of kernel1 before the update, and between the two convolutions the quotient (as the rows / planes of its x-spectrum) by
+     * the reach of kernel2; interior sides carry max(k1/2, k2/2) only, i.e. less redundant FFT volume.  Scheme 1 needs an attached
+     * exchange (mvd_comm_attach or mvd_set_exchange_callback), one FFT tile per context, and does not support the Mul iteration.   */
+    int exchange_scheme;
 } mvd_config;
 
 MVD_API const char* mvd_last_error(void);                     /* thread-local message of the last failing call          */
@@ -179,6 +185,21 @@ MVD_API int mvd_comm_create(const char id[128], int world, int rank, int device,
 MVD_API int mvd_comm_destroy(mvd_comm* comm);
 MVD_API int mvd_comm_attach(mvd_context* ctx, mvd_comm* comm, int py, int pz);
 MVD_API int mvd_exchange_halos(mvd_context* ctx);
+/* Host-provided exchange instead of NCCL (a JVM copying between its contexts with cudaMemcpyPeer, MPI, the CPU tests).  The box is a
+ * [nplanes][nrows][row_floats] float array in the context's memory space with the own region rows [y0,y1) x planes [z0,z1); the
+ * callback must fill hy_lo rows below / hy_hi rows above the own rows over the own planes from the y neighbours, THEN hz_lo / hz_hi
+ * whole planes (all rows, fresh y halos included) from the z neighbours -- and serve the neighbours symmetrically: the neighbour below
+ * wants this box's first h*_hi own rows / planes, the one above its last h*_lo.  which: 0 = psi, 1 = x-spectrum of the quotient
+ * (scheme 1).  The context's stream is synchronised before the call; the data must be in place when the callback returns 0.          */
+typedef struct mvd_halo_box {
+    float* base;
+    long long row_floats;
+    int nrows, nplanes;
+    int y0, y1, z0, z1;
+    int hy_lo, hy_hi, hz_lo, hz_hi;
+} mvd_halo_box;
+typedef int (*mvd_exchange_fn)(void* user, int which, const mvd_halo_box* box);
+MVD_API int mvd_set_exchange_callback(mvd_context* ctx, mvd_exchange_fn fn, void* user);
 
 /* Per-pass device timing (CUDA events on the context's stream around every pass launch): slots 0..8 = passes P1..P9 of a
  * view update.  ms[] are accumulated milliseconds, counts[] the number of launches; reset != 0 clears them.   */

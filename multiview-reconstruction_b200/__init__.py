@@ -52,7 +52,18 @@ class _Config(C.Structure):
     _fields_ = [("device", C.c_int), ("dims", C.c_int * 3), ("num_views", C.c_int), ("psf_type", C.c_int),
                 ("lambda_", C.c_float), ("min_value", C.c_float), ("shard_lo", C.c_int), ("shard_hi", C.c_int),
                 ("local_z0", C.c_int), ("local_nz", C.c_int), ("max_fft_len", C.c_int), ("norm_quirk_threads", C.c_int),
-                ("shard_y_lo", C.c_int), ("shard_y_hi", C.c_int), ("local_y0", C.c_int), ("local_ny", C.c_int)]
+                ("shard_y_lo", C.c_int), ("shard_y_hi", C.c_int), ("local_y0", C.c_int), ("local_ny", C.c_int),
+                ("exchange_scheme", C.c_int)]
+
+
+class HaloBox(C.Structure):
+    """mvd_halo_box: a [nplanes][nrows][row_floats] float array, the own region inside it and the halo widths to fill"""
+    _fields_ = [("base", C.POINTER(C.c_float)), ("row_floats", C.c_longlong), ("nrows", C.c_int), ("nplanes", C.c_int),
+                ("y0", C.c_int), ("y1", C.c_int), ("z0", C.c_int), ("z1", C.c_int),
+                ("hy_lo", C.c_int), ("hy_hi", C.c_int), ("hz_lo", C.c_int), ("hz_hi", C.c_int)]
+
+
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(HaloBox))
 
 
 _F = C.POINTER(C.c_float)
@@ -105,6 +116,7 @@ SYMBOLS = {
     "mvd_comm_create": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "mvd_comm_destroy": (C.c_int, [C.c_void_p]),
     "mvd_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "mvd_set_exchange_callback": (C.c_int, [C.c_void_p, EXCHANGE_FN, C.c_void_p]),
     "mvd_exchange_halos": (C.c_int, [C.c_void_p]),
     "mvd_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "mvd_get_pass_times": (C.c_int, [C.c_void_p, _D, C.POINTER(C.c_longlong), C.c_int]),
@@ -310,7 +322,8 @@ class DeconViews:
     def __init__(self, views: Sequence[DeconView], device: int = 0, lambda_: float = 0.0, min_value: float = minValue,
                  shard: Optional[Tuple[int, int, int, int]] = None, global_dims_zyx: Optional[Sequence[int]] = None,
                  shard_y: Optional[Tuple[int, int, int, int]] = None,
-                 max_fft_len: int = 0, norm_quirk_threads: int = 0, async_upload: bool = False, library: Optional[Lib] = None):
+                 max_fft_len: int = 0, norm_quirk_threads: int = 0, async_upload: bool = False, library: Optional[Lib] = None,
+                 exchange_scheme: int = 0):
         self.lib = library or lib()
         self.views = list(views)
         if not self.views:
@@ -338,6 +351,7 @@ class DeconViews:
             cfg.shard_y_lo, cfg.shard_y_hi, cfg.local_y0, cfg.local_ny = (int(x) for x in shard_y)
         cfg.max_fft_len = int(max_fft_len)
         cfg.norm_quirk_threads = int(norm_quirk_threads)      # 0 = exact sums; T reproduces AdjustInput.sumImg for T threads
+        cfg.exchange_scheme = int(exchange_scheme)            # sharded contexts: 0 = psi exchange only, 1 = psi + quotient exchange
         self._ctx = C.c_void_p()
         self.lib.check(self.lib.dll.mvd_create(C.byref(cfg), C.byref(self._ctx)))
         try:
@@ -430,6 +444,20 @@ class DeconViews:
         """attach the in-library NCCL halo exchange for a py x pz (y x z) grid, rank = ry * pz + rz"""
         self.lib.check(self.lib.dll.mvd_comm_attach(self._ctx, comm.handle, int(py), int(pz)))
         self._comm = comm
+
+    def set_exchange_callback(self, fn):
+        """host-provided halo exchange: fn(which, box: HaloBox) is called with the context's stream synchronised (which 0 = psi,
+        1 = x-spectrum of the quotient); exceptions make the library call fail"""
+        def tramp(_user, which, box):
+            try:
+                fn(int(which), box.contents)
+                return 0
+            except Exception:  # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._exchange_cb = EXCHANGE_FN(tramp)                # keep the trampoline alive as long as the context
+        self.lib.check(self.lib.dll.mvd_set_exchange_callback(self._ctx, self._exchange_cb, None))
 
     def exchange_halos(self):
         self.lib.check(self.lib.dll.mvd_exchange_halos(self._ctx))

@@ -69,6 +69,8 @@ int mvd_create(const mvd_config* cfg, mvd_context** out) {
         c.min_value = cfg->min_value;
         c.max_len = cfg->max_fft_len > 0 ? cfg->max_fft_len : 1152;
         c.norm_quirk_threads = cfg->norm_quirk_threads > 0 ? cfg->norm_quirk_threads : 0;
+        require(cfg->exchange_scheme == 0 || cfg->exchange_scheme == 1, "exchange_scheme must be 0 or 1");
+        c.exchange_scheme = cfg->exchange_scheme;
         require(cfg->psf_type >= 0 && cfg->psf_type <= 3, "bad psf_type");
         Geometry& g = c.geom;
         for (int d = 0; d < 3; ++d) {
@@ -251,6 +253,13 @@ int mvd_comm_destroy(mvd_comm* comm) {
 }
 int mvd_comm_attach(mvd_context* ctx, mvd_comm* comm, int py, int pz) {
     return guarded([&] { require(ctx && comm, "null argument"); ctx->engine->comm_attach(comm->comm, py, pz); });
+}
+static_assert(sizeof(mvd_halo_box) == sizeof(HaloBox), "mvd_halo_box mirrors HaloBox");
+int mvd_set_exchange_callback(mvd_context* ctx, mvd_exchange_fn fn, void* user) {
+    return guarded([&] {
+        require(ctx != nullptr, "null argument");
+        ctx->engine->set_exchange_callback(reinterpret_cast<ExchangeFn>(fn), user);
+    });
 }
 int mvd_exchange_halos(mvd_context* ctx) {
     return guarded([&] { require(ctx, "null context"); ctx->engine->exchange_halos(); });

@@ -5,6 +5,8 @@
 // plumbing (torch.distributed in bench.py, a socket / MPI elsewhere).
 #include "engine.h"
 
+#include <cstdint>
+
 #ifndef MVD_HOST_EMU
 #include <dlfcn.h>
 #endif
@@ -48,17 +50,30 @@ constexpr int kNcclFloat = 7;
 
 #endif
 
-// copy rows [ya, ya+rows) of planes [za, za+planes) between the local volume and a dense staging buffer
+// copy rows [ya, ya+rows) of planes [za, za+planes) between the array and a dense staging buffer (float4 granules when aligned)
+template <typename T>
 struct PackRows {
-    float* vol; float* stage; int nx, ny, ya, za, rows; int to_stage;
+    T* vol; T* stage; long long nx; int ny, ya, za, rows; int to_stage;
     MVD_HD void operator()(long long i) const {
-        const int x = (int)(i % nx);
+        const long long x = i % nx;
         const long long r = i / nx;
         const int y = (int)(r % rows), z = (int)(r / rows);
         const long long vi = ((long long)(za + z) * ny + (ya + y)) * nx + x;
         if (to_stage) stage[i] = vol[vi]; else vol[vi] = stage[i];
     }
 };
+struct Quad { float a, b, c, d; };
+static void pack_rows(const HaloBox& b, float* stage, int ya, int rows, int to_stage, stream_t s) {
+    const int planes = b.z1 - b.z0;
+    if (rows <= 0 || planes <= 0) return;
+    if (b.row_floats % 4 == 0 && ((uintptr_t)b.base % 16) == 0 && ((uintptr_t)stage % 16) == 0) {
+        PackRows<Quad> p{(Quad*)b.base, (Quad*)stage, b.row_floats / 4, b.nrows, ya, b.z0, rows, to_stage};
+        pfor((long long)rows * p.nx * planes, p, s);
+    } else {
+        PackRows<float> p{b.base, stage, b.row_floats, b.nrows, ya, b.z0, rows, to_stage};
+        pfor((long long)rows * p.nx * planes, p, s);
+    }
+}
 
 void NcclComm::unique_id(char out[128]) {
 #ifndef MVD_HOST_EMU
@@ -91,60 +106,74 @@ NcclComm::~NcclComm() {
 #endif
 }
 
-HaloComm::HaloComm(std::shared_ptr<NcclComm> comm, int py, int pz, const Geometry& g, int halo_y, int halo_z, stream_t s)
-    : comm_(std::move(comm)), py_(py), pz_(pz), g_(g), hy_(halo_y), hz_(halo_z), stream_(s) {
-    if (!comm_ || py * pz != comm_->world()) throw Error("bad process grid");
+HaloComm::HaloComm(std::shared_ptr<NcclComm> comm, int py, int pz, stream_t s)
+    : comm_(std::move(comm)), py_(py), pz_(pz), stream_(s) {
+    if (!comm_ || py < 1 || pz < 1 || py * pz != comm_->world()) throw Error("bad process grid");
     ry_ = comm_->rank() / pz; rz_ = comm_->rank() % pz;
-    if (py > 1) {
-        const size_t n = (size_t)hy_ * g.vol[0] * (size_t)(g.own_hi[2] - g.own_lo[2]);
-        for (int i = 0; i < 4; ++i) stage_[i] = (float*)dev::alloc(sizeof(float) * n);
-    }
 }
 
 HaloComm::~HaloComm() {
     for (float* p : stage_) dev::free_(p);
 }
 
-void HaloComm::exchange(float* psi) {
+void HaloComm::reserve(size_t floats) {
+    if (floats <= stage_floats_) return;
+    dev::sync(stream_);
+    for (float*& p : stage_) { dev::free_(p); p = (float*)dev::alloc(sizeof(float) * floats); }
+    stage_floats_ = floats;
+}
+
+// Neighbour below (ry-1 / rz-1): it needs my first h*_hi own rows / planes (its upper halo) and sends its last h*_lo ones (my lower
+// halo); the neighbour above mirrors that.  The widths are the same on every rank (they come from the kernel extents).
+void HaloComm::exchange(const HaloBox& b) {
 #ifndef MVD_HOST_EMU
     NcclApi& n = nccl();
-    const int nx = g_.vol[0], ny = g_.vol[1];
-    const int ylo = g_.own_lo[1] - g_.goff[1], yhi = g_.own_hi[1] - g_.goff[1];       // local indices
-    const int zlo = g_.own_lo[2] - g_.goff[2], zhi = g_.own_hi[2] - g_.goff[2];
-    if (py_ > 1) {
-        const int planes = zhi - zlo;
-        const long long cnt = (long long)hy_ * nx * planes;
+    ncclComm_t c = (ncclComm_t)comm_->raw();
+    if (py_ > 1 && (b.hy_lo > 0 || b.hy_hi > 0)) {
         const bool lower = ry_ > 0, upper = ry_ < py_ - 1;
-        if (lower) pfor(cnt, PackRows{psi, stage_[0], nx, ny, ylo, zlo, hy_, 1}, stream_);
-        if (upper) pfor(cnt, PackRows{psi, stage_[1], nx, ny, yhi - hy_, zlo, hy_, 1}, stream_);
+        if ((lower && (b.y0 - b.hy_lo < 0 || b.y0 + b.hy_hi > b.y1)) || (upper && (b.y1 + b.hy_hi > b.nrows || b.y1 - b.hy_lo < b.y0)))
+            throw Error("halo exchange: the array does not contain the halo rows");
+        const size_t per_row = (size_t)b.row_floats * (size_t)(b.z1 - b.z0);
+        reserve((size_t)std::max(b.hy_lo, b.hy_hi) * per_row);
+        const size_t cnt_lo = (size_t)b.hy_lo * per_row, cnt_hi = (size_t)b.hy_hi * per_row;
+        if (lower) pack_rows(b, stage_[0], b.y0, b.hy_hi, 1, stream_);
+        if (upper) pack_rows(b, stage_[1], b.y1 - b.hy_lo, b.hy_lo, 1, stream_);
         nccl_check(n.GroupStart(), "group");
         if (lower) {
-            nccl_check(n.Send(stage_[0], (size_t)cnt, kNcclFloat, (ry_ - 1) * pz_ + rz_, (ncclComm_t)comm_->raw(), stream_), "send");
-            nccl_check(n.Recv(stage_[2], (size_t)cnt, kNcclFloat, (ry_ - 1) * pz_ + rz_, (ncclComm_t)comm_->raw(), stream_), "recv");
+            const int peer = (ry_ - 1) * pz_ + rz_;
+            if (cnt_hi) nccl_check(n.Send(stage_[0], cnt_hi, kNcclFloat, peer, c, stream_), "send");
+            if (cnt_lo) nccl_check(n.Recv(stage_[2], cnt_lo, kNcclFloat, peer, c, stream_), "recv");
         }
         if (upper) {
-            nccl_check(n.Send(stage_[1], (size_t)cnt, kNcclFloat, (ry_ + 1) * pz_ + rz_, (ncclComm_t)comm_->raw(), stream_), "send");
-            nccl_check(n.Recv(stage_[3], (size_t)cnt, kNcclFloat, (ry_ + 1) * pz_ + rz_, (ncclComm_t)comm_->raw(), stream_), "recv");
+            const int peer = (ry_ + 1) * pz_ + rz_;
+            if (cnt_lo) nccl_check(n.Send(stage_[1], cnt_lo, kNcclFloat, peer, c, stream_), "send");
+            if (cnt_hi) nccl_check(n.Recv(stage_[3], cnt_hi, kNcclFloat, peer, c, stream_), "recv");
         }
         nccl_check(n.GroupEnd(), "group");
-        if (lower) pfor(cnt, PackRows{psi, stage_[2], nx, ny, ylo - hy_, zlo, hy_, 0}, stream_);
-        if (upper) pfor(cnt, PackRows{psi, stage_[3], nx, ny, yhi, zlo, hy_, 0}, stream_);
+        if (lower) pack_rows(b, stage_[2], b.y0 - b.hy_lo, b.hy_lo, 0, stream_);
+        if (upper) pack_rows(b, stage_[3], b.y1, b.hy_hi, 0, stream_);
     }
-    if (pz_ > 1) {
-        const size_t plane = (size_t)nx * ny, cnt = plane * hz_;
+    if (pz_ > 1 && (b.hz_lo > 0 || b.hz_hi > 0)) {
+        const bool lower = rz_ > 0, upper = rz_ < pz_ - 1;
+        if ((lower && (b.z0 - b.hz_lo < 0 || b.z0 + b.hz_hi > b.z1)) || (upper && (b.z1 + b.hz_hi > b.nplanes || b.z1 - b.hz_lo < b.z0)))
+            throw Error("halo exchange: the array does not contain the halo planes");
+        const size_t plane = (size_t)b.row_floats * (size_t)b.nrows;
+        const size_t cnt_lo = plane * b.hz_lo, cnt_hi = plane * b.hz_hi;
         nccl_check(n.GroupStart(), "group");
-        if (rz_ > 0) {
-            nccl_check(n.Send(psi + plane * zlo, cnt, kNcclFloat, ry_ * pz_ + rz_ - 1, (ncclComm_t)comm_->raw(), stream_), "send");
-            nccl_check(n.Recv(psi + plane * (zlo - hz_), cnt, kNcclFloat, ry_ * pz_ + rz_ - 1, (ncclComm_t)comm_->raw(), stream_), "recv");
+        if (lower) {
+            const int peer = ry_ * pz_ + rz_ - 1;
+            if (cnt_hi) nccl_check(n.Send(b.base + plane * b.z0, cnt_hi, kNcclFloat, peer, c, stream_), "send");
+            if (cnt_lo) nccl_check(n.Recv(b.base + plane * (b.z0 - b.hz_lo), cnt_lo, kNcclFloat, peer, c, stream_), "recv");
         }
-        if (rz_ < pz_ - 1) {
-            nccl_check(n.Send(psi + plane * (zhi - hz_), cnt, kNcclFloat, ry_ * pz_ + rz_ + 1, (ncclComm_t)comm_->raw(), stream_), "send");
-            nccl_check(n.Recv(psi + plane * zhi, cnt, kNcclFloat, ry_ * pz_ + rz_ + 1, (ncclComm_t)comm_->raw(), stream_), "recv");
+        if (upper) {
+            const int peer = ry_ * pz_ + rz_ + 1;
+            if (cnt_lo) nccl_check(n.Send(b.base + plane * (b.z1 - b.hz_lo), cnt_lo, kNcclFloat, peer, c, stream_), "send");
+            if (cnt_hi) nccl_check(n.Recv(b.base + plane * b.z1, cnt_hi, kNcclFloat, peer, c, stream_), "recv");
         }
         nccl_check(n.GroupEnd(), "group");
     }
 #else
-    (void)psi;
+    (void)b;
 #endif
 }
 

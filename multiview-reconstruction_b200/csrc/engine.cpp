@@ -63,7 +63,7 @@ const cpx* Tables::twist(int M) {
 // tile edge.  Outside the global volume the quotient is known to be 1 (no image data), which is why tiles that
 // contain a volume boundary only need the single-convolution margin there.
 // ------------------------------------------------------------------------------------------------
-AxisTiling plan_axis(int gdim, int a, int b, Reach r1, Reach r2, bool is_x, int max_len) {
+AxisTiling plan_axis(int gdim, int a, int b, Reach r1, Reach r2, bool is_x, int max_len, bool two_exchanges) {
     const int Lsum = r1.lo + r2.lo, Rsum = r1.hi + r2.hi;
     const int Lmax = std::max(r1.lo, r2.lo), Rmax = std::max(r1.hi, r2.hi);
     AxisTiling best;
@@ -77,11 +77,12 @@ AxisTiling plan_axis(int gdim, int a, int b, Reach r1, Reach r2, bool is_x, int 
         AxisTiling cur;
         cur.T = T;
         int pos = a;
-        int o = (a == 0) ? -Lmax : a - Lsum;
+        // a shard boundary behaves like a volume face when the quotient is exchanged too (scheme B): one reach is enough
+        int o = (a == 0 || two_exchanges) ? a - Lmax : a - Lsum;
         bool ok = true;
         while (pos < b) {
             int vend = o + T - Rsum;
-            if (b == gdim && o + T >= gdim + Rmax) vend = b;
+            if ((b == gdim || two_exchanges) && o + T >= b + Rmax) vend = b;
             const int hi = std::min(vend, b);
             if (hi <= pos || cur.tiles.size() > 65536) { ok = false; break; }
             cur.tiles.push_back(AxisTile{o, pos, hi});
@@ -138,7 +139,8 @@ struct ReduceParts2 {
 // ------------------------------------------------------------------------------------------------
 // Convolver
 // ------------------------------------------------------------------------------------------------
-Convolver::Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], int xmode, int max_len, stream_t s, Tables* tables)
+Convolver::Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], int xmode, int max_len, stream_t s, Tables* tables,
+                     bool two_exchanges)
     : g_(g), xmode_(xmode), stream_(s), tables_(tables) {
     if (const char* e = std::getenv("MVD_PREFETCH_DIST")) pf_x_ = pf_y_ = pf_z_ = std::atoi(e);
     if (const char* e = std::getenv("MVD_PF_X")) pf_x_ = std::atoi(e);
@@ -153,7 +155,10 @@ Convolver::Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], in
         }
         M_ = ax[0].T;
     } else {
-        for (int d = 0; d < 3; ++d) ax[d] = plan_axis(g.gdim[d], g.own_lo[d], g.own_hi[d], r1[d], r2[d], d == 0, max_len);
+        for (int d = 0; d < 3; ++d) {
+            const bool shard = g.own_lo[d] != 0 || g.own_hi[d] != g.gdim[d];
+            ax[d] = plan_axis(g.gdim[d], g.own_lo[d], g.own_hi[d], r1[d], r2[d], d == 0, max_len, two_exchanges && shard);
+        }
         M_ = ax[0].T / 2;
     }
     for (int d = 0; d < 3; ++d) T_[d] = ax[d].T;
@@ -315,7 +320,12 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
             mark(3); col(1, COL_INV, nullptr, z0, z1);    // P4
             a.src = img;                                  // P5: quotient, 1 where there is no image data
             mark(4); xpass(X_RATIO, a, z0, z1);
-            mark(5); col(1, COL_FWD, nullptr, z0, z1);    // P6
+            if (!mid_exchange_) { mark(5); col(1, COL_FWD, nullptr, z0, z1); }   // P6
+        }
+        if (mid_exchange_) {                              // scheme B: the neighbours' quotient rows / planes arrive as x-spectra
+            mark(-1);
+            mid_exchange_(work_, t);
+            for (int z0 = 0; z0 < T_[2]; z0 += cp) { mark(5); col(1, COL_FWD, nullptr, z0, std::min(T_[2], z0 + cp)); }
         }
         mark(6); col(2, COL_CONV, k2hat);                 // P7
         a.src = psi_in;                                   // P9
@@ -585,16 +595,25 @@ void Engine::init_views() {
             r2[d].lo = std::max(r2[d].lo, b.lo); r2[d].hi = std::max(r2[d].hi, b.hi);
         }
     }
-    halo_lo_ = cfg_.geom.own_lo[2] == 0 ? 0 : r1[2].lo + r2[2].lo;
-    halo_hi_ = cfg_.geom.own_hi[2] == cfg_.geom.gdim[2] ? 0 : r1[2].hi + r2[2].hi;
+    for (int d = 0; d < 3; ++d) { r1_[d] = r1[d]; r2_[d] = r2[d]; }
+    const bool two = cfg_.exchange_scheme == 1;
+    auto need = [&](int d, bool lower) {
+        const int a = lower ? r1[d].lo : r1[d].hi, b = lower ? r2[d].lo : r2[d].hi;
+        return two ? std::max(a, b) : a + b;
+    };
+    halo_lo_ = cfg_.geom.own_lo[2] == 0 ? 0 : need(2, true);
+    halo_hi_ = cfg_.geom.own_hi[2] == cfg_.geom.gdim[2] ? 0 : need(2, false);
     if (cfg_.geom.own_lo[2] - halo_lo_ < cfg_.geom.goff[2] || cfg_.geom.own_hi[2] + halo_hi_ > cfg_.geom.goff[2] + cfg_.geom.vol[2])
-        throw Error("sharded context: the local arrays do not contain the halo planes (k1z/2 + k2z/2 per interior side)");
-    halo_y_lo_ = cfg_.geom.own_lo[1] == 0 ? 0 : r1[1].lo + r2[1].lo;
-    halo_y_hi_ = cfg_.geom.own_hi[1] == cfg_.geom.gdim[1] ? 0 : r1[1].hi + r2[1].hi;
+        throw Error("sharded context: the local arrays do not contain the halo planes (mvd_halo_planes)");
+    halo_y_lo_ = cfg_.geom.own_lo[1] == 0 ? 0 : need(1, true);
+    halo_y_hi_ = cfg_.geom.own_hi[1] == cfg_.geom.gdim[1] ? 0 : need(1, false);
     if (cfg_.geom.own_lo[1] - halo_y_lo_ < cfg_.geom.goff[1] || cfg_.geom.own_hi[1] + halo_y_hi_ > cfg_.geom.goff[1] + cfg_.geom.vol[1])
-        throw Error("sharded context: the local arrays do not contain the halo rows (k1y/2 + k2y/2 per interior side)");
+        throw Error("sharded context: the local arrays do not contain the halo rows (mvd_halo_rows)");
     for (View& vw : views_) { dev::free_(vw.k1hat); dev::free_(vw.k2hat); vw.k1hat = vw.k2hat = nullptr; }
-    conv_.reset(new Convolver(cfg_.geom, r1, r2, 0, cfg_.max_len, stream_, tables_.get()));
+    conv_.reset(new Convolver(cfg_.geom, r1, r2, 0, cfg_.max_len, stream_, tables_.get(), two));
+    if (two && (sharded(1) || sharded(2)) && conv_->num_tiles() != 1)
+        throw Error("exchange scheme 1 needs the local box to fit one FFT tile (use scheme 0 or more ranks)");
+    install_mid_exchange();
     for (View& vw : views_) {
         vw.k1hat = conv_->build_khat(vw.k1.data(), vw.k1d);
         vw.k2hat = conv_->build_khat(vw.k2.data(), vw.k2d);
@@ -772,6 +791,7 @@ void Engine::iteration_mul() {
     if (V > MVD_MAX_VIEWS) throw Error("too many views");
     const Geometry& g = cfg_.geom;
     if (g.own_lo[1] != 0 || g.own_hi[1] != g.gdim[1]) throw Error("the Mul iteration supports z-slab sharding only");
+    if (cfg_.exchange_scheme == 1 && sharded(2)) throw Error("the Mul iteration needs exchange scheme 0");
     const long long plane = (long long)g.vol[0] * g.vol[1], n = (long long)local_voxels();
     const long long own0 = (long long)(g.own_lo[2] - g.goff[2]) * plane, own1 = (long long)(g.own_hi[2] - g.goff[2]) * plane;
     if ((int)integral_.size() < V) {
@@ -796,7 +816,7 @@ void Engine::iteration_mul() {
                 stats_dev_ + 2 * (size_t)stats_count_, max_dev_);
     ++stats_count_;
     cur_ ^= 1;
-    if (comm_) comm_->exchange(psi_[cur_]);
+    if (has_exchange()) exchange_psi(psi_[cur_]);
 }
 
 void Engine::view_update(int v) {
@@ -805,6 +825,8 @@ void Engine::view_update(int v) {
     dev::set_device(cfg_.device);
     View& vw = views_[v];
     if (!vw.img || !vw.weight) throw Error("view without image/weight");
+    if (cfg_.exchange_scheme == 1 && (sharded(1) || sharded(2)) && !has_exchange())
+        throw Error("exchange scheme 1: attach a communicator (mvd_comm_attach) or an exchange callback before the first view update");
     if (vw.pending) { dev::stream_wait(stream_, vw.ready); vw.pending = false; }
     ensure_stats_slot();
     const int nparts = conv_->num_tiles() * conv_->parts_per_tile();
@@ -817,23 +839,63 @@ void Engine::view_update(int v) {
     pfor(1, r2, stream_);
     ++stats_count_;
     cur_ ^= 1;
-    if (comm_) comm_->exchange(psi_[cur_]);
+    if (has_exchange()) exchange_psi(psi_[cur_]);
 }
 
 void Engine::comm_attach(std::shared_ptr<NcclComm> comm, int py, int pz) {
     if (!inited_) throw Error("init_views() must run before the communicator is attached (the halo widths come from the kernels)");
     if (!comm || comm->device() != cfg_.device) throw Error("communicator belongs to another device");
     dev::set_device(cfg_.device);
-    const Geometry& g = cfg_.geom;
-    const bool ysh = g.own_lo[1] != 0 || g.own_hi[1] != g.gdim[1], zsh = g.own_lo[2] != 0 || g.own_hi[2] != g.gdim[2];
-    if ((py > 1) != ysh || (pz > 1) != zsh) throw Error("process grid does not match the sharding of this context");
-    const int hy = std::max(halo_y_lo_, halo_y_hi_), hz = std::max(halo_lo_, halo_hi_);
-    comm_.reset(new HaloComm(std::move(comm), py, pz, g, hy, hz, stream_));
+    if ((py > 1) != sharded(1) || (pz > 1) != sharded(2)) throw Error("process grid does not match the sharding of this context");
+    comm_.reset(new HaloComm(std::move(comm), py, pz, stream_));
+    install_mid_exchange();
 }
+
+void Engine::do_exchange(int which, const HaloBox& b) {
+    if (host_exchange_) {
+        dev::sync(stream_);
+        if (host_exchange_(host_exchange_user_, which, &b) != 0) throw Error("the host's exchange callback failed");
+    } else if (comm_) {
+        comm_->exchange(b);
+    }
+}
+
+// psi: scheme 0 ships what both convolutions read beyond the own box (r1 + r2), scheme 1 only the first convolution's reach
+void Engine::exchange_psi(float* psi) {
+    const Geometry& g = cfg_.geom;
+    const bool two = cfg_.exchange_scheme == 1;
+    HaloBox b;
+    b.base = psi; b.row_floats = g.vol[0]; b.nrows = g.vol[1]; b.nplanes = g.vol[2];
+    b.y0 = g.own_lo[1] - g.goff[1]; b.y1 = g.own_hi[1] - g.goff[1];
+    b.z0 = g.own_lo[2] - g.goff[2]; b.z1 = g.own_hi[2] - g.goff[2];
+    b.hy_lo = sharded(1) ? r1_[1].lo + (two ? 0 : r2_[1].lo) : 0; b.hy_hi = sharded(1) ? r1_[1].hi + (two ? 0 : r2_[1].hi) : 0;
+    b.hz_lo = sharded(2) ? r1_[2].lo + (two ? 0 : r2_[2].lo) : 0; b.hz_hi = sharded(2) ? r1_[2].hi + (two ? 0 : r2_[2].hi) : 0;
+    do_exchange(0, b);
+}
+
+// scheme 1: between the two convolutions the quotient of the neighbours' own boxes replaces this box's halo rows / planes.  The
+// quotient only exists as its x-spectrum (P5 fuses inverse-x -> quotient -> forward-x); the x transform is per row, so the rows and
+// planes of the spectrum are exchanged instead -- same geometry, rows of 2 * pitch floats.
+void Engine::install_mid_exchange() {
+    if (!conv_) return;
+    if (cfg_.exchange_scheme != 1 || !(sharded(1) || sharded(2)) || !has_exchange()) { conv_->set_mid_exchange(nullptr); return; }
+    conv_->set_mid_exchange([this](cpx* work, const TileGeom& t) {
+        const Geometry& g = cfg_.geom;
+        const int* T = conv_->tile_dims();
+        HaloBox b;
+        b.base = reinterpret_cast<float*>(work); b.row_floats = 2LL * conv_->pitch(); b.nrows = T[1]; b.nplanes = T[2];
+        b.y0 = g.own_lo[1] - t.org[1]; b.y1 = g.own_hi[1] - t.org[1];
+        b.z0 = g.own_lo[2] - t.org[2]; b.z1 = g.own_hi[2] - t.org[2];
+        b.hy_lo = sharded(1) ? r2_[1].lo : 0; b.hy_hi = sharded(1) ? r2_[1].hi : 0;
+        b.hz_lo = sharded(2) ? r2_[2].lo : 0; b.hz_hi = sharded(2) ? r2_[2].hi : 0;
+        do_exchange(1, b);
+    });
+}
+
 void Engine::exchange_halos() {
-    if (!comm_) throw Error("no communicator attached (mvd_comm_attach)");
+    if (!has_exchange()) throw Error("no communicator attached (mvd_comm_attach / mvd_set_exchange_callback)");
     dev::set_device(cfg_.device);
-    comm_->exchange(psi_[cur_]);
+    exchange_psi(psi_[cur_]);
 }
 
 void Engine::fetch_stats(int count, IterStats* out) {

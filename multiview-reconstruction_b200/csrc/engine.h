@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include <functional>
+
 #include "backend.h"
 
 namespace mvd {
@@ -55,8 +57,14 @@ class Convolver {
   public:
     // r1: reach of the first convolution, r2: reach of the second (all zero for a single convolution).
     // xmode 0: negacyclic real-packed x axis (halo'd tiles); xmode 1: exact circular convolution at the volume size
-    Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], int xmode, int max_len, stream_t s, Tables* tables);
+    // two_exchanges: the sharded sides of the box only carry max(r1, r2) (scheme B: the host exchanges psi by r1 before the update
+    // and the quotient by r2 between the two convolutions, see set_mid_exchange) instead of r1 + r2 (scheme A)
+    Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], int xmode, int max_len, stream_t s, Tables* tables,
+              bool two_exchanges = false);
     ~Convolver();
+    // called between P5 and P6 of a view update with the tile's x-spectrum of the quotient ([Tz][Ty][px] complex)
+    void set_mid_exchange(std::function<void(cpx* work, const TileGeom& t)> f) { mid_exchange_ = std::move(f); }
+    int pitch() const { return px_; }
 
     size_t tile_elems() const { return (size_t)px_ * T_[1] * T_[2]; }            // complex elements per spectrum
     int num_tiles() const { return (int)tiles_.size(); }
@@ -98,6 +106,7 @@ class Convolver {
     Tables* tables_;
     cpx* work_ = nullptr;
     float* kpad_ = nullptr;
+    std::function<void(cpx*, const TileGeom&)> mid_exchange_;
     // software L2 prefetch distance in CTAs for the x, y and z passes (MVD_PF_X / MVD_PF_Y / MVD_PF_Z override)
     int pf_x_ = 74, pf_y_ = 296, pf_z_ = 148;
     int chunk_planes_ = 0;  // planes per L2-resident chunk of the x/y pass chains (0 = whole tile per launch)
@@ -111,7 +120,7 @@ class Convolver {
     long long prof_n_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
-AxisTiling plan_axis(int gdim, int own_lo, int own_hi, Reach r1, Reach r2, bool is_x, int max_len);
+AxisTiling plan_axis(int gdim, int own_lo, int own_hi, Reach r1, Reach r2, bool is_x, int max_len, bool two_exchanges = false);
 
 // dst = src (*) kernel on the device; host in / host out.  circular: exact circular convolution at the volume size (legacy
 // JNA semantics), otherwise U/FFTConvolution semantics (output = size of src, src extended by ext).
@@ -134,17 +143,28 @@ class NcclComm {                         // one communicator per process and dev
     void* comm_ = nullptr;
     int world_, rank_, device_;
 };
+// a [planes][rows][row_floats] float array with this instance's own region inside it, and the widths of the halo to fill below /
+// above the own region along y (rows) and z (planes).  Mirrors mvd_halo_box of the C ABI.
+struct HaloBox {
+    float* base;
+    long long row_floats;
+    int nrows, nplanes;
+    int y0, y1, z0, z1;                  // own region, array indices, half open
+    int hy_lo, hy_hi, hz_lo, hz_hi;      // halo rows / planes wanted below (lo) and above (hi) the own region
+};
+typedef int (*ExchangeFn)(void* user, int which, const HaloBox* box);      // host-provided exchange (mvd_exchange_fn)
+
 class HaloComm {
   public:
-    HaloComm(std::shared_ptr<NcclComm> comm, int py, int pz, const Geometry& g, int halo_y, int halo_z, stream_t s);
+    HaloComm(std::shared_ptr<NcclComm> comm, int py, int pz, stream_t s);
     ~HaloComm();
-    void exchange(float* psi);          // enqueued on the stream; the host does not block
+    void exchange(const HaloBox& b);     // enqueued on the stream; the host does not block
   private:
+    void reserve(size_t floats);
     std::shared_ptr<NcclComm> comm_;
     int py_, pz_, ry_ = 0, rz_ = 0;
-    Geometry g_;
-    int hy_, hz_;
     stream_t stream_;
+    size_t stage_floats_ = 0;
     float* stage_[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -176,6 +196,7 @@ class Engine {
         float min_value = 1e-4f;
         int max_len = 1152;
         int norm_quirk_threads = 0;   // 0: exact kernel sums; T > 0: reproduce AdjustInput.sumImg's double count for T threads
+        int exchange_scheme = 0;      // sharded contexts: 0 = one psi exchange per view update (halo r1 + r2), 1 = psi (r1) + quotient (r2)
     };
     explicit Engine(const Config& c);
     ~Engine();
@@ -213,6 +234,8 @@ class Engine {
     void iteration_mul();
     // attach the NCCL halo exchange: afterwards every view update / Mul iteration is followed by the exchange of the new psi
     void comm_attach(std::shared_ptr<NcclComm> comm, int py, int pz);
+    // host-provided exchange instead of NCCL (the stream is synchronised before every call; see mvd_set_exchange_callback)
+    void set_exchange_callback(ExchangeFn fn, void* user) { host_exchange_ = fn; host_exchange_user_ = user; install_mid_exchange(); }
     void exchange_halos();
     void view_update(int v);                               // asynchronous on the engine stream
     void fetch_stats(int count, IterStats* out);           // last `count` view updates (synchronises)
@@ -262,6 +285,14 @@ class Engine {
     double* stats_dev_ = nullptr;   // ring of {sum,max} pairs
     void ensure_stats_slot();
     std::unique_ptr<HaloComm> comm_;
+    ExchangeFn host_exchange_ = nullptr;
+    void* host_exchange_user_ = nullptr;
+    Reach r1_[3] = {{0, 0}, {0, 0}, {0, 0}}, r2_[3] = {{0, 0}, {0, 0}, {0, 0}};     // kernel reaches (max over views)
+    bool sharded(int d) const { return cfg_.geom.own_lo[d] != 0 || cfg_.geom.own_hi[d] != cfg_.geom.gdim[d]; }
+    bool has_exchange() const { return comm_ != nullptr || host_exchange_ != nullptr; }
+    void do_exchange(int which, const HaloBox& b);
+    void exchange_psi(float* psi);
+    void install_mid_exchange();
     std::vector<float*> integral_;  // Mul iteration: one integral volume per view
     double* lut_dev_ = nullptr;     // cosine blending LUT
     double* acc_dev_ = nullptr;     // {sum, count} scratch

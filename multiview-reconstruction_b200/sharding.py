@@ -40,15 +40,17 @@ def exchange_halos(buf, plane: int, lo: int, hi: int, z0: int, halo: int, rank: 
 # ---------------------------------------------------------------------------------------------------------------------
 # 2-d (y x z) process grid
 # ---------------------------------------------------------------------------------------------------------------------
-def axis_cost(n: int, lo: int, hi: int, reach: int, lengths) -> int:
+def axis_cost(n: int, lo: int, hi: int, reach: int, lengths, scheme: int = 0) -> int:
     """FFT-box extent (tiles * T) the engine's planner needs to cover [lo, hi) of an axis of size n when each of the two chained
-    convolutions reaches `reach` samples (mirrors plan_axis in csrc/engine.cpp; halo per interior side = 2 * reach)."""
+    convolutions reaches `reach` samples (mirrors plan_axis in csrc/engine.cpp; halo per interior side = 2 * reach with exchange
+    scheme 0, reach with scheme 1)."""
     best = None
+    two = scheme == 1 and (lo != 0 or hi != n)
     for T in lengths:
-        pos, o, tiles, ok = lo, (-reach if lo == 0 else lo - 2 * reach), 0, True
+        pos, o, tiles, ok = lo, (lo - reach if (lo == 0 or two) else lo - 2 * reach), 0, True
         while pos < hi:
             vend = o + T - 2 * reach
-            if hi == n and o + T >= n + reach:
+            if (hi == n or two) and o + T >= hi + reach:
                 vend = hi
             nxt = min(vend, hi)
             if nxt <= pos:
@@ -63,7 +65,7 @@ def axis_cost(n: int, lo: int, hi: int, reach: int, lengths) -> int:
     return best
 
 
-def grid_for(world: int, ny: int, nz: int, reach_y: int, reach_z: int, lengths) -> Tuple[int, int]:
+def grid_for(world: int, ny: int, nz: int, reach_y: int, reach_z: int, lengths, scheme: int = 0) -> Tuple[int, int]:
     """(py, pz) with py * pz == world minimising the FFT-box volume of the slowest rank, evaluated with the library's real tile
     lengths (Lib.supported_fft_lengths()).  At equal cost the larger py wins: the single-GPU plan already splits y into FFT tiles,
     so the first y split is free."""
@@ -74,8 +76,8 @@ def grid_for(world: int, ny: int, nz: int, reach_y: int, reach_z: int, lengths) 
         pz = world // py
         if ny // py <= 4 * reach_y or nz // pz <= 4 * reach_z:
             continue
-        cy = max(axis_cost(ny, *slab_range(ny, py, r), reach_y, lengths) for r in range(py))
-        cz = max(axis_cost(nz, *slab_range(nz, pz, r), reach_z, lengths) for r in range(pz))
+        cy = max(axis_cost(ny, *slab_range(ny, py, r), reach_y, lengths, scheme) for r in range(py))
+        cz = max(axis_cost(nz, *slab_range(nz, pz, r), reach_z, lengths, scheme) for r in range(pz))
         key = (cy * cz, -py)
         if best is None or key < best[0]:
             best = (key, (py, pz))
@@ -121,3 +123,70 @@ def exchange_halos_2d(buf3, own_y, loc_y, own_z, loc_z, halo_y, halo_z, ry, rz, 
             ops += [dist.P2POp(dist.isend, buf3[zhi - z0 - halo_z:zhi - z0], peer), dist.P2POp(dist.irecv, buf3[zhi - z0:zhi - z0 + halo_z], peer)]
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+
+
+def exchange_box(t3, own_y, own_z, halo_y, halo_z, ry, rz, py, pz, rank_of, dist) -> None:
+    """Generic two-phase exchange on a tensor [planes, rows, row_floats] (the body of an mvd_exchange_fn callback): own_* = (lo, hi)
+    array indices of the own region, halo_* = (below, above) widths.  The neighbour below gets this box's first `above` own rows /
+    planes and sends its last `below` ones; the neighbour above mirrors that.  y rows travel over the own planes only, then whole z
+    planes including the fresh y halos (corners)."""
+    y0, y1 = own_y
+    z0, z1 = own_z
+    hl, hu = halo_y
+    if py > 1 and (hl or hu):
+        zs = slice(z0, z1)
+        ops, recvs = [], []
+        for present, peer_ry, send_rows, recv_rows in ((ry > 0, ry - 1, slice(y0, y0 + hu), slice(y0 - hl, y0)),
+                                                       (ry < py - 1, ry + 1, slice(y1 - hl, y1), slice(y1, y1 + hu))):
+            if not present:
+                continue
+            peer = rank_of(peer_ry, rz)
+            if send_rows.stop > send_rows.start:
+                ops.append(dist.P2POp(dist.isend, t3[zs, send_rows, :].contiguous(), peer))
+            if recv_rows.stop > recv_rows.start:
+                rb = t3.new_empty((z1 - z0, recv_rows.stop - recv_rows.start, t3.shape[2]))
+                ops.append(dist.P2POp(dist.irecv, rb, peer))
+                recvs.append((rb, recv_rows))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for rb, rows in recvs:
+            t3[zs, rows, :] = rb
+    hl, hu = halo_z
+    if pz > 1 and (hl or hu):
+        ops = []
+        for present, peer_rz, send_pl, recv_pl in ((rz > 0, rz - 1, slice(z0, z0 + hu), slice(z0 - hl, z0)),
+                                                   (rz < pz - 1, rz + 1, slice(z1 - hl, z1), slice(z1, z1 + hu))):
+            if not present:
+                continue
+            peer = rank_of(ry, peer_rz)
+            if send_pl.stop > send_pl.start:
+                ops.append(dist.P2POp(dist.isend, t3[send_pl], peer))
+            if recv_pl.stop > recv_pl.start:
+                ops.append(dist.P2POp(dist.irecv, t3[recv_pl], peer))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+
+def host_exchange_callback(ry, rz, py, pz, rank_of, dist, device=None):
+    """An exchange callback for DeconViews.set_exchange_callback built on torch.distributed: wraps the library's buffer (host memory
+    for the CPU emulator, device memory otherwise) as a tensor and runs exchange_box on it."""
+    import ctypes
+
+    import numpy as np
+    import torch
+
+    def cb(which, box):
+        n = box.nplanes * box.nrows * box.row_floats
+        if device is None:
+            arr = np.ctypeslib.as_array(box.base, shape=(n,))
+            t3 = torch.from_numpy(arr).view(box.nplanes, box.nrows, box.row_floats)
+        else:
+            from . import RawDeviceBuffer
+            ptr = ctypes.cast(box.base, ctypes.c_void_p).value
+            t3 = torch.as_tensor(RawDeviceBuffer(ptr, (box.nplanes, box.nrows, box.row_floats)), device=device)
+        exchange_box(t3, (box.y0, box.y1), (box.z0, box.z1), (box.hy_lo, box.hy_hi), (box.hz_lo, box.hz_hi), ry, rz, py, pz, rank_of, dist)
+        if device is not None:
+            torch.cuda.synchronize(device)
+    return cb

@@ -407,8 +407,8 @@ def test_two_devices_in_one_process(product_lib, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("axis", ["z", "y"])
-def test_in_library_halo_exchange_two_gpus(product_lib, oracle, axis):
+@pytest.mark.parametrize("axis,scheme", [("z", 0), ("y", 0), ("z", 1), ("y", 1)])
+def test_in_library_halo_exchange_two_gpus(product_lib, oracle, axis, scheme):
     """two contexts on two devices joined by the library's own NCCL exchange (mvd_comm_create / mvd_comm_attach): mvd_run_iterations
     on each shard, without any host-side exchange, must equal the whole-volume update"""
     if product_lib.getNumDevicesCUDA() < 2:
@@ -420,7 +420,8 @@ def test_in_library_halo_exchange_two_gpus(product_lib, oracle, axis):
     mx = [v.max_intensity for v in views]
     nz, ny = 48, 40
     n = nz if axis == "z" else ny
-    cut, H = n // 2 + 3, 8
+    cut = n // 2 + 3
+    H = (3 if scheme == 1 else 6) if axis == "y" else (2 if scheme == 1 else 4)        # PSF 5 x 7 x 5 (x, y, z)
     uid = product_lib.comm_unique_id()
     res, err = {}, []
 
@@ -432,7 +433,8 @@ def test_in_library_halo_exchange_two_gpus(product_lib, oracle, axis):
             loc = [m.DeconView(np.ascontiguousarray(ds.images[v][sl]), np.ascontiguousarray(ds.weights[v][sl]), ds.psfs[v],
                                m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(2)]
             kw = {"shard": (lo, hi, a0, a1 - a0)} if axis == "z" else {"shard_y": (lo, hi, a0, a1 - a0)}
-            d = m.DeconViews(loc, global_dims_zyx=(nz, ny, 36), device=r, **kw)
+            d = m.DeconViews(loc, global_dims_zyx=(nz, ny, 36), device=r, exchange_scheme=scheme, **kw)
+            assert (d.halo_planes() if axis == "z" else d.halo_rows()) == ((0, H) if r == 0 else (H, 0))
             comm = product_lib.comm_create(uid, 2, r, r)
             d.comm_attach(comm, *((1, 2) if axis == "z" else (2, 1)))
             dec = m.MultiViewDeconvolutionSeq(d, 2, m.PsiInitFromRAI(np.ascontiguousarray(psi0[sl]), mx))

@@ -112,3 +112,71 @@ def test_process_grid_prefers_y_first():
     py, pz = sharding.grid_for(8, 1024, 512, 9, 12, lengths)
     assert py * pz == 8 and py >= 2
     assert sharding.axis_cost(1024, 0, 1024, 9, lengths) == 1080 and sharding.axis_cost(512, 0, 512, 12, lengths) == 540
+
+
+# ---- exchange callback (mvd_set_exchange_callback) and exchange scheme 1 (psi + quotient exchange) ---------------------------------
+DIMS_CB = (40, 28, 24)
+KW_CB = dict(psf_size_xyz=(5, 5, 5), psf_sigma_xyz=(1.0, 1.1, 1.3), bead_density=512)
+
+
+def _worker_cb(rank, world, port, lib_path, out_dir, axis, scheme):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch.distributed as dist
+    import mvdecon_oracle as o
+    import mvrecon_b200 as m
+    from mvrecon_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = m.Lib(lib_path)
+    ds = o.make_synthetic(DIMS_CB, VIEWS, seed=6, **KW_CB)
+    views, psi0, avg = o.make_oracle_views(ds, o.EFFICIENT_BAYESIAN)
+    n = DIMS_CB[0] if axis == "z" else DIMS_CB[1]
+    reach = 2                                                   # (5 - 1) / 2 for kernel1 and kernel2
+    H = reach if scheme == 1 else 2 * reach
+    lo, hi = sharding.slab_range(n, world, rank)
+    a0, a1 = sharding.extended_range(lo, hi, n, H)
+    sl = (slice(a0, a1),) if axis == "z" else (slice(None), slice(a0, a1))
+    loc = [m.DeconView(np.ascontiguousarray(ds.images[v][sl]), np.ascontiguousarray(ds.weights[v][sl]), ds.psfs[v],
+                       m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(VIEWS)]
+    kw = {"shard": (lo, hi, a0, a1 - a0)} if axis == "z" else {"shard_y": (lo, hi, a0, a1 - a0)}
+    dv = m.DeconViews(loc, global_dims_zyx=DIMS_CB, library=lib, exchange_scheme=scheme, **kw)
+    want = ((0 if rank == 0 else H), (0 if rank == world - 1 else H))
+    assert (dv.halo_planes() if axis == "z" else dv.halo_rows()) == want
+    py, pz = (1, world) if axis == "z" else (world, 1)
+    ry, rz = (0, rank) if axis == "z" else (rank, 0)
+    calls = []
+    inner = sharding.host_exchange_callback(ry, rz, py, pz, lambda a, b: a * pz + b, dist)
+
+    def cb(which, box):
+        calls.append(which)
+        inner(which, box)
+
+    dec = m.MultiViewDeconvolutionSeq(dv, 2, m.PsiInitFromRAI(np.ascontiguousarray(psi0[sl]), [v.max_intensity for v in views]))
+    if scheme == 1:
+        with pytest.raises(m.MvdError, match="exchange scheme 1"):
+            dv.enqueue_view_update(0)
+    dv.set_exchange_callback(cb)
+    dec.runIterations()                                         # the library calls back for every exchange: no host-side loop
+    assert calls == ([0] * 4 if scheme == 0 else [1, 0] * 4)
+    own = (slice(lo - a0, hi - a0),) if axis == "z" else (slice(None), slice(lo - a0, hi - a0))
+    np.save(os.path.join(out_dir, f"part{rank}.npy"), dec.getPSI()[own])
+    dv.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("axis,scheme", [("z", 0), ("z", 1), ("y", 1)])
+def test_exchange_callback_and_two_exchange_scheme(hostemu_lib, oracle, tmp_path, axis, scheme):
+    import torch.multiprocessing as mp
+    world = 2
+    port = 31500 + (os.getpid() % 2000) + 7 * scheme + (3 if axis == "y" else 0)
+    mp.start_processes(_worker_cb, args=(world, port, hostemu_lib.path, str(tmp_path), axis, scheme), nprocs=world, join=True,
+                       start_method="spawn")
+    ds = oracle.make_synthetic(DIMS_CB, VIEWS, seed=6, **KW_CB)
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN)
+    ref, _ = oracle.run_iterations_seq(psi0, views, 2, 0.0, dtype=np.float64)
+    got = np.concatenate([np.load(tmp_path / f"part{r}.npy") for r in range(world)], axis=0 if axis == "z" else 1)
+    assert got.shape == ref.shape
+    assert oracle.rel_l2(got, ref) < 4e-6
