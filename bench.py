@@ -363,6 +363,7 @@ def run_ours(args):
                 exchange()
 
     attach_comm(dv)
+    transport = dv.exchange_transport() if use_lib_comm else ("torch.distributed" if world > 1 else "none")
 
     for _ in range(args.warmup):
         one_iteration()
@@ -403,7 +404,7 @@ def run_ours(args):
     if args.skip_e2e:
         if rank == 0:
             print(json.dumps({"metric": "voxel*view*iterations/s", "value": value, "n_gpus": world, "ms_per_step": ms / args.steps,
-                              "note": "profiling run (--skip-e2e): not a bench line",
+                              "note": "profiling run (--skip-e2e): not a bench line", "transport": transport,
                               "all_passes_ms_per_launch": [round(a / max(b, 1), 4) for a, b in zip(pass_ms, pass_n)]}))
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
@@ -469,7 +470,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[name], "step": f"one OSEM iteration = {V} view updates over the whole volume",
                        "fft_tile_xyz": info["tile_dims_xyz"], "tiles_per_gpu": info["num_tiles"], "fft_box_over_useful_voxels": round(info["fft_volume_ratio"], 4),
-                       "sharding": "none" if world == 1 else f"{py} x {pz} (y x z) boxes, exchange scheme {scheme} (" + ("psi by k1/2 before + quotient spectrum by k2/2 inside" if scheme == 1 else "psi by k1/2 + k2/2 after") + f" every view update; local halo {Hy} rows / {Hz} planes), NCCL send/recv enqueued on the compute stream " + ("by the library" if use_lib_comm else "by torch.distributed"),
+                       "sharding": "none" if world == 1 else f"{py} x {pz} (y x z) boxes, exchange scheme {scheme} (" + ("psi by k1/2 before + quotient spectrum by k2/2 inside" if scheme == 1 else "psi by k1/2 + k2/2 after") + f" every view update; local halo {Hy} rows / {Hz} planes), enqueued on the compute stream " + ("by the library" if use_lib_comm else "by torch.distributed") + f", transport {transport}",
                        "l2_flush": "not needed: every pass streams >= 1.2 GB (inputs larger than the 126 MB L2)",
                        "roofline_fraction_92B": value * B_ALG / (peak * 1e9 * world), "output_finite": finite},
             "roofline": {"bound": "hbm", "kernel": PASS_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -185,6 +185,9 @@ MVD_API int mvd_comm_create(const char id[128], int world, int rank, int device,
 MVD_API int mvd_comm_destroy(mvd_comm* comm);
 MVD_API int mvd_comm_attach(mvd_context* ctx, mvd_comm* comm, int py, int pz);
 MVD_API int mvd_exchange_halos(mvd_context* ctx);
+/* How the halos travel: -1 no exchange attached, 0 NCCL send/recv, 1 direct stores into the neighbours' HBM over NVLink (CUDA IPC /
+ * peer access; chosen automatically when every rank can map its neighbours, MVD_EXCHANGE=nccl forces 0), 2 host callback.          */
+MVD_API int mvd_exchange_transport(mvd_context* ctx, int* transport);
 /* Host-provided exchange instead of NCCL (a JVM copying between its contexts with cudaMemcpyPeer, MPI, the CPU tests).  The box is a
  * [nplanes][nrows][row_floats] float array in the context's memory space with the own region rows [y0,y1) x planes [z0,z1); the
  * callback must fill hy_lo rows below / hy_hi rows above the own rows over the own planes from the y neighbours, THEN hz_lo / hz_hi

@@ -117,6 +117,7 @@ SYMBOLS = {
     "mvd_comm_destroy": (C.c_int, [C.c_void_p]),
     "mvd_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mvd_set_exchange_callback": (C.c_int, [C.c_void_p, EXCHANGE_FN, C.c_void_p]),
+    "mvd_exchange_transport": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "mvd_exchange_halos": (C.c_int, [C.c_void_p]),
     "mvd_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "mvd_get_pass_times": (C.c_int, [C.c_void_p, _D, C.POINTER(C.c_longlong), C.c_int]),
@@ -461,6 +462,11 @@ class DeconViews:
 
     def exchange_halos(self):
         self.lib.check(self.lib.dll.mvd_exchange_halos(self._ctx))
+
+    def exchange_transport(self) -> str:
+        t = C.c_int()
+        self.lib.check(self.lib.dll.mvd_exchange_transport(self._ctx, C.byref(t)))
+        return {-1: "none", 0: "nccl", 1: "peer-stores", 2: "host-callback"}[t.value]
 
     def enqueue_view_update(self, v: int):
         self.lib.check(self.lib.dll.mvd_enqueue_view_update(self._ctx, int(v)))

@@ -261,6 +261,9 @@ int mvd_set_exchange_callback(mvd_context* ctx, mvd_exchange_fn fn, void* user) 
         ctx->engine->set_exchange_callback(reinterpret_cast<ExchangeFn>(fn), user);
     });
 }
+int mvd_exchange_transport(mvd_context* ctx, int* transport) {
+    return guarded([&] { require(ctx && transport, "null argument"); *transport = ctx->engine->exchange_transport(); });
+}
 int mvd_exchange_halos(mvd_context* ctx) {
     return guarded([&] { require(ctx, "null context"); ctx->engine->exchange_halos(); });
 }

@@ -9,6 +9,7 @@
 
 #ifndef MVD_HOST_EMU
 #include <dlfcn.h>
+#include <unistd.h>
 #endif
 
 namespace mvd {
@@ -27,6 +28,7 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi& nccl() {
@@ -38,14 +40,14 @@ NcclApi& nccl() {
 #define MVD_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, name)); if (!api.field) throw Error("NCCL symbol missing: " name);
     MVD_SYM(GetUniqueId, "ncclGetUniqueId") MVD_SYM(CommInitRank, "ncclCommInitRank") MVD_SYM(CommDestroy, "ncclCommDestroy")
     MVD_SYM(GroupStart, "ncclGroupStart") MVD_SYM(GroupEnd, "ncclGroupEnd") MVD_SYM(Send, "ncclSend") MVD_SYM(Recv, "ncclRecv")
-    MVD_SYM(GetErrorString, "ncclGetErrorString")
+    MVD_SYM(GetErrorString, "ncclGetErrorString") MVD_SYM(AllGather, "ncclAllGather")
 #undef MVD_SYM
     return api;
 }
 void nccl_check(ncclResult_t r, const char* what) {
     if (r != 0) throw Error(std::string("NCCL ") + what + ": " + nccl().GetErrorString(r));
 }
-constexpr int kNcclFloat = 7;
+constexpr int kNcclFloat = 7, kNcclChar = 0;
 }  // namespace
 
 #endif
@@ -62,7 +64,7 @@ struct PackRows {
         if (to_stage) stage[i] = vol[vi]; else vol[vi] = stage[i];
     }
 };
-struct Quad { float a, b, c, d; };
+struct alignas(16) Quad { float a, b, c, d; };
 static void pack_rows(const HaloBox& b, float* stage, int ya, int rows, int to_stage, stream_t s) {
     const int planes = b.z1 - b.z0;
     if (rows <= 0 || planes <= 0) return;
@@ -106,14 +108,16 @@ NcclComm::~NcclComm() {
 #endif
 }
 
-HaloComm::HaloComm(std::shared_ptr<NcclComm> comm, int py, int pz, stream_t s)
+HaloComm::HaloComm(std::shared_ptr<NcclComm> comm, int py, int pz, stream_t s, size_t need_y, size_t need_z)
     : comm_(std::move(comm)), py_(py), pz_(pz), stream_(s) {
     if (!comm_ || py < 1 || pz < 1 || py * pz != comm_->world()) throw Error("bad process grid");
     ry_ = comm_->rank() / pz; rz_ = comm_->rank() % pz;
+    setup_peer(need_y, need_z);
 }
 
 HaloComm::~HaloComm() {
     for (float* p : stage_) dev::free_(p);
+    close_peer();
 }
 
 void HaloComm::reserve(size_t floats) {
@@ -123,16 +127,27 @@ void HaloComm::reserve(size_t floats) {
     stage_floats_ = floats;
 }
 
+static void check_box(const HaloBox& b, bool ylower, bool yupper, bool zlower, bool zupper) {
+    if ((ylower && (b.y0 - b.hy_lo < 0 || b.y0 + b.hy_hi > b.y1)) || (yupper && (b.y1 + b.hy_hi > b.nrows || b.y1 - b.hy_lo < b.y0)))
+        throw Error("halo exchange: the array does not contain the halo rows");
+    if ((zlower && (b.z0 - b.hz_lo < 0 || b.z0 + b.hz_hi > b.z1)) || (zupper && (b.z1 + b.hz_hi > b.nplanes || b.z1 - b.hz_lo < b.z0)))
+        throw Error("halo exchange: the array does not contain the halo planes");
+}
+
+void HaloComm::exchange(const HaloBox& b) {
+    const bool ydo = py_ > 1 && (b.hy_lo > 0 || b.hy_hi > 0), zdo = pz_ > 1 && (b.hz_lo > 0 || b.hz_hi > 0);
+    check_box(b, ydo && ry_ > 0, ydo && ry_ < py_ - 1, zdo && rz_ > 0, zdo && rz_ < pz_ - 1);
+    if (peer_) exchange_peer(b); else exchange_nccl(b);
+}
+
 // Neighbour below (ry-1 / rz-1): it needs my first h*_hi own rows / planes (its upper halo) and sends its last h*_lo ones (my lower
 // halo); the neighbour above mirrors that.  The widths are the same on every rank (they come from the kernel extents).
-void HaloComm::exchange(const HaloBox& b) {
+void HaloComm::exchange_nccl(const HaloBox& b) {
 #ifndef MVD_HOST_EMU
     NcclApi& n = nccl();
     ncclComm_t c = (ncclComm_t)comm_->raw();
     if (py_ > 1 && (b.hy_lo > 0 || b.hy_hi > 0)) {
         const bool lower = ry_ > 0, upper = ry_ < py_ - 1;
-        if ((lower && (b.y0 - b.hy_lo < 0 || b.y0 + b.hy_hi > b.y1)) || (upper && (b.y1 + b.hy_hi > b.nrows || b.y1 - b.hy_lo < b.y0)))
-            throw Error("halo exchange: the array does not contain the halo rows");
         const size_t per_row = (size_t)b.row_floats * (size_t)(b.z1 - b.z0);
         reserve((size_t)std::max(b.hy_lo, b.hy_hi) * per_row);
         const size_t cnt_lo = (size_t)b.hy_lo * per_row, cnt_hi = (size_t)b.hy_hi * per_row;
@@ -155,8 +170,6 @@ void HaloComm::exchange(const HaloBox& b) {
     }
     if (pz_ > 1 && (b.hz_lo > 0 || b.hz_hi > 0)) {
         const bool lower = rz_ > 0, upper = rz_ < pz_ - 1;
-        if ((lower && (b.z0 - b.hz_lo < 0 || b.z0 + b.hz_hi > b.z1)) || (upper && (b.z1 + b.hz_hi > b.nplanes || b.z1 - b.hz_lo < b.z0)))
-            throw Error("halo exchange: the array does not contain the halo planes");
         const size_t plane = (size_t)b.row_floats * (size_t)b.nrows;
         const size_t cnt_lo = plane * b.hz_lo, cnt_hi = plane * b.hz_hi;
         nccl_check(n.GroupStart(), "group");
@@ -171,6 +184,182 @@ void HaloComm::exchange(const HaloBox& b) {
             if (cnt_hi) nccl_check(n.Recv(b.base + plane * b.z1, cnt_hi, kNcclFloat, peer, c, stream_), "recv");
         }
         nccl_check(n.GroupEnd(), "group");
+    }
+#else
+    (void)b;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// peer transport: the halo rows / planes are stored straight into a landing buffer in the neighbour's HBM over NVLink (no NCCL
+// FIFO, no proxy, no staging on the sending side), followed by a release of an arrival counter in the neighbour's memory; the
+// receiver spins on its own counter and unpacks the landing buffer locally.  Landing buffers alternate with the exchange parity:
+// exchange s+2 can only be pushed after the neighbour's push of s+1 arrived, which it enqueued after unpacking s.
+// ------------------------------------------------------------------------------------------------------------------------------
+float* HaloComm::landing(float* region, int src, int parity) const {
+    return src < 2 ? region + (size_t)(src * 2 + parity) * cap_y_ : region + 4 * cap_y_ + (size_t)((src - 2) * 2 + parity) * cap_z_;
+}
+unsigned* HaloComm::flags(float* region) const { return reinterpret_cast<unsigned*>(region + 4 * cap_y_ + 4 * cap_z_); }
+
+struct SignalArrival {     // runs after the push kernels of this stream completed, i.e. after their stores were performed
+    volatile unsigned* flag; unsigned seq;
+    MVD_HD void operator()(long long) const {
+#if defined(__CUDA_ARCH__)
+        __threadfence_system();
+#endif
+        *flag = seq;
+    }
+};
+struct AwaitArrival {
+    volatile unsigned* f0; volatile unsigned* f1; unsigned seq;
+    MVD_HD void operator()(long long) const {
+#if defined(__CUDA_ARCH__)
+        unsigned long long t0, t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (int k = 0; k < 2; ++k) {
+            volatile unsigned* f = k == 0 ? f0 : f1;
+            if (!f) continue;
+            while ((int)(*f - seq) < 0) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t - t0 > 30000000000ULL) __trap();            // a neighbour died: fail loudly instead of hanging the device
+                __nanosleep(64);
+            }
+        }
+        __threadfence_system();
+#endif
+    }
+};
+struct CopyQuads {
+    const Quad* src; Quad* dst;
+    MVD_HD void operator()(long long i) const { dst[i] = src[i]; }
+};
+
+#ifndef MVD_HOST_EMU
+namespace {
+struct PeerInfo {
+    cudaIpcMemHandle_t handle;
+    unsigned long long pid, ptr, need_y, need_z;
+    int device, ok;
+};
+// byte-wise all-gather of one small record per rank through the communicator
+template <class T>
+std::vector<T> gather_records(const T& mine, NcclComm& comm, stream_t s) {
+    const int W = comm.world();
+    char* d = (char*)dev::alloc(sizeof(T) * (size_t)(W + 1));
+    dev::h2d(d, &mine, sizeof(T), s);
+    nccl_check(nccl().AllGather(d, d + sizeof(T), sizeof(T), kNcclChar, (ncclComm_t)comm.raw(), s), "allgather");
+    std::vector<T> all((size_t)W);
+    dev::d2h(all.data(), d + sizeof(T), sizeof(T) * (size_t)W, s);
+    dev::sync(s);
+    dev::free_(d);
+    return all;
+}
+}  // namespace
+#endif
+
+void HaloComm::setup_peer(size_t need_y, size_t need_z) {
+#ifndef MVD_HOST_EMU
+    if (const char* e = std::getenv("MVD_EXCHANGE")) if (std::string(e) == "nccl") return;      // A/B switch
+    if (comm_->world() == 1) return;
+    // round 1: sizes.  Every landing buffer gets the largest push any rank will ever make (multiple of 64 floats = 256 B).
+    PeerInfo me;
+    std::memset(&me, 0, sizeof(me));
+    me.pid = (unsigned long long)getpid();
+    me.device = comm_->device();
+    me.need_y = need_y; me.need_z = need_z;
+    std::vector<PeerInfo> all = gather_records(me, *comm_, stream_);
+    for (const PeerInfo& p : all) { cap_y_ = std::max(cap_y_, (size_t)p.need_y); cap_z_ = std::max(cap_z_, (size_t)p.need_z); }
+    cap_y_ = (cap_y_ + 63) / 64 * 64; cap_z_ = (cap_z_ + 63) / 64 * 64;
+    const size_t bytes = sizeof(float) * (4 * cap_y_ + 4 * cap_z_) + 256;
+    int ok = 1;
+    if (cudaMalloc((void**)&region_, bytes) != cudaSuccess) { cudaGetLastError(); region_ = nullptr; ok = 0; }
+    if (ok) {
+        MVD_CUDA_CHECK(cudaMemsetAsync(flags(region_), 0, 256, stream_));
+        dev::sync(stream_);
+        if (cudaIpcGetMemHandle(&me.handle, region_) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
+    me.ptr = (unsigned long long)(uintptr_t)region_;
+    me.ok = ok;
+    // round 2: handles; map the (up to four) neighbours
+    all = gather_records(me, *comm_, stream_);
+    const int nb_rank[4] = {ry_ > 0 ? (ry_ - 1) * pz_ + rz_ : -1, ry_ < py_ - 1 ? (ry_ + 1) * pz_ + rz_ : -1,
+                            rz_ > 0 ? ry_ * pz_ + rz_ - 1 : -1, rz_ < pz_ - 1 ? ry_ * pz_ + rz_ + 1 : -1};
+    for (int i = 0; i < 4 && ok; ++i) {
+        if (nb_rank[i] < 0) continue;
+        const PeerInfo& p = all[(size_t)nb_rank[i]];
+        if (!p.ok) { ok = 0; break; }
+        if (p.pid == me.pid) {                               // neighbour context in this process: plain peer access
+            if (p.device != me.device) {
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, me.device, p.device) != cudaSuccess || !can) { cudaGetLastError(); ok = 0; break; }
+                const cudaError_t e = cudaDeviceEnablePeerAccess(p.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ok = 0; break; }
+                cudaGetLastError();
+            }
+            nb_region_[i] = reinterpret_cast<float*>((uintptr_t)p.ptr);
+        } else {
+            void* q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, p.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            nb_region_[i] = (float*)q;
+            nb_ipc_[i] = true;
+        }
+    }
+    // round 3: every rank must have mapped its neighbours, otherwise all stay on NCCL
+    me.ok = ok;
+    all = gather_records(me, *comm_, stream_);
+    for (const PeerInfo& p : all) ok = ok && p.ok;
+    if (!ok) { close_peer(); return; }
+    peer_ = true;
+#else
+    (void)need_y; (void)need_z;
+#endif
+}
+
+void HaloComm::close_peer() {
+#ifndef MVD_HOST_EMU
+    for (int i = 0; i < 4; ++i) {
+        if (nb_region_[i] && nb_ipc_[i]) cudaIpcCloseMemHandle(nb_region_[i]);
+        nb_region_[i] = nullptr; nb_ipc_[i] = false;
+    }
+    if (region_) cudaFree(region_);
+    region_ = nullptr;
+    peer_ = false;
+#endif
+}
+
+void HaloComm::exchange_peer(const HaloBox& b) {
+#ifndef MVD_HOST_EMU
+    ++seq_;
+    const int par = (int)(seq_ & 1u);
+    unsigned* mine = flags(region_);
+    if (py_ > 1 && (b.hy_lo > 0 || b.hy_hi > 0)) {
+        const bool lower = ry_ > 0, upper = ry_ < py_ - 1;
+        const size_t per_row = (size_t)b.row_floats * (size_t)(b.z1 - b.z0);
+        if ((size_t)std::max(b.hy_lo, b.hy_hi) * per_row > cap_y_) throw Error("halo exchange: landing buffer too small (y)");
+        // I am the lower neighbour's UPPER neighbour: my first hy_hi own rows land in its "from upper y" buffer (src 1), and vice versa
+        if (lower) { pack_rows(b, landing(nb_region_[0], 1, par), b.y0, b.hy_hi, 1, stream_); pfor(1, SignalArrival{flags(nb_region_[0]) + 1, seq_}, stream_); }
+        if (upper) { pack_rows(b, landing(nb_region_[1], 0, par), b.y1 - b.hy_lo, b.hy_lo, 1, stream_); pfor(1, SignalArrival{flags(nb_region_[1]) + 0, seq_}, stream_); }
+        if (lower || upper) pfor(1, AwaitArrival{lower ? mine + 0 : nullptr, upper ? mine + 1 : nullptr, seq_}, stream_);
+        if (lower) pack_rows(b, landing(region_, 0, par), b.y0 - b.hy_lo, b.hy_lo, 0, stream_);
+        if (upper) pack_rows(b, landing(region_, 1, par), b.y1, b.hy_hi, 0, stream_);
+    }
+    if (pz_ > 1 && (b.hz_lo > 0 || b.hz_hi > 0)) {
+        const bool lower = rz_ > 0, upper = rz_ < pz_ - 1;
+        const size_t plane = (size_t)b.row_floats * (size_t)b.nrows;
+        if (plane * (size_t)std::max(b.hz_lo, b.hz_hi) > cap_z_) throw Error("halo exchange: landing buffer too small (z)");
+        if (plane % 4 != 0 || ((uintptr_t)b.base % 16) != 0) throw Error("halo exchange: unaligned planes");
+        const long long q_lo = (long long)(plane * b.hz_lo / 4), q_hi = (long long)(plane * b.hz_hi / 4);
+        if (lower) {
+            pfor(q_hi, CopyQuads{(const Quad*)(b.base + plane * b.z0), (Quad*)landing(nb_region_[2], 3, par)}, stream_);
+            pfor(1, SignalArrival{flags(nb_region_[2]) + 3, seq_}, stream_);
+        }
+        if (upper) {
+            pfor(q_lo, CopyQuads{(const Quad*)(b.base + plane * (b.z1 - b.hz_lo)), (Quad*)landing(nb_region_[3], 2, par)}, stream_);
+            pfor(1, SignalArrival{flags(nb_region_[3]) + 2, seq_}, stream_);
+        }
+        if (lower || upper) pfor(1, AwaitArrival{lower ? mine + 2 : nullptr, upper ? mine + 3 : nullptr, seq_}, stream_);
+        if (lower) pfor(q_lo, CopyQuads{(const Quad*)landing(region_, 2, par), (Quad*)(b.base + plane * (b.z0 - b.hz_lo))}, stream_);
+        if (upper) pfor(q_hi, CopyQuads{(const Quad*)landing(region_, 3, par), (Quad*)(b.base + plane * b.z1)}, stream_);
     }
 #else
     (void)b;

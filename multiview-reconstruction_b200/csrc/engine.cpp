@@ -847,7 +847,14 @@ void Engine::comm_attach(std::shared_ptr<NcclComm> comm, int py, int pz) {
     if (!comm || comm->device() != cfg_.device) throw Error("communicator belongs to another device");
     dev::set_device(cfg_.device);
     if ((py > 1) != sharded(1) || (pz > 1) != sharded(2)) throw Error("process grid does not match the sharding of this context");
-    comm_.reset(new HaloComm(std::move(comm), py, pz, stream_));
+    size_t need_y = 0, need_z = 0;
+    auto account = [&](const HaloBox& b) {
+        need_y = std::max(need_y, (size_t)std::max(b.hy_lo, b.hy_hi) * (size_t)b.row_floats * (size_t)(b.z1 - b.z0));
+        need_z = std::max(need_z, (size_t)std::max(b.hz_lo, b.hz_hi) * (size_t)b.row_floats * (size_t)b.nrows);
+    };
+    account(psi_box(psi_[0]));
+    if (cfg_.exchange_scheme == 1) account(spectrum_box(nullptr, conv_->tiles().at(0)));
+    comm_.reset(new HaloComm(std::move(comm), py, pz, stream_, need_y, need_z));
     install_mid_exchange();
 }
 
@@ -861,7 +868,7 @@ void Engine::do_exchange(int which, const HaloBox& b) {
 }
 
 // psi: scheme 0 ships what both convolutions read beyond the own box (r1 + r2), scheme 1 only the first convolution's reach
-void Engine::exchange_psi(float* psi) {
+HaloBox Engine::psi_box(float* psi) const {
     const Geometry& g = cfg_.geom;
     const bool two = cfg_.exchange_scheme == 1;
     HaloBox b;
@@ -870,26 +877,28 @@ void Engine::exchange_psi(float* psi) {
     b.z0 = g.own_lo[2] - g.goff[2]; b.z1 = g.own_hi[2] - g.goff[2];
     b.hy_lo = sharded(1) ? r1_[1].lo + (two ? 0 : r2_[1].lo) : 0; b.hy_hi = sharded(1) ? r1_[1].hi + (two ? 0 : r2_[1].hi) : 0;
     b.hz_lo = sharded(2) ? r1_[2].lo + (two ? 0 : r2_[2].lo) : 0; b.hz_hi = sharded(2) ? r1_[2].hi + (two ? 0 : r2_[2].hi) : 0;
-    do_exchange(0, b);
+    return b;
 }
+void Engine::exchange_psi(float* psi) { do_exchange(0, psi_box(psi)); }
 
 // scheme 1: between the two convolutions the quotient of the neighbours' own boxes replaces this box's halo rows / planes.  The
 // quotient only exists as its x-spectrum (P5 fuses inverse-x -> quotient -> forward-x); the x transform is per row, so the rows and
 // planes of the spectrum are exchanged instead -- same geometry, rows of 2 * pitch floats.
+HaloBox Engine::spectrum_box(cpx* work, const TileGeom& t) const {
+    const Geometry& g = cfg_.geom;
+    const int* T = conv_->tile_dims();
+    HaloBox b;
+    b.base = reinterpret_cast<float*>(work); b.row_floats = 2LL * conv_->pitch(); b.nrows = T[1]; b.nplanes = T[2];
+    b.y0 = g.own_lo[1] - t.org[1]; b.y1 = g.own_hi[1] - t.org[1];
+    b.z0 = g.own_lo[2] - t.org[2]; b.z1 = g.own_hi[2] - t.org[2];
+    b.hy_lo = sharded(1) ? r2_[1].lo : 0; b.hy_hi = sharded(1) ? r2_[1].hi : 0;
+    b.hz_lo = sharded(2) ? r2_[2].lo : 0; b.hz_hi = sharded(2) ? r2_[2].hi : 0;
+    return b;
+}
 void Engine::install_mid_exchange() {
     if (!conv_) return;
     if (cfg_.exchange_scheme != 1 || !(sharded(1) || sharded(2)) || !has_exchange()) { conv_->set_mid_exchange(nullptr); return; }
-    conv_->set_mid_exchange([this](cpx* work, const TileGeom& t) {
-        const Geometry& g = cfg_.geom;
-        const int* T = conv_->tile_dims();
-        HaloBox b;
-        b.base = reinterpret_cast<float*>(work); b.row_floats = 2LL * conv_->pitch(); b.nrows = T[1]; b.nplanes = T[2];
-        b.y0 = g.own_lo[1] - t.org[1]; b.y1 = g.own_hi[1] - t.org[1];
-        b.z0 = g.own_lo[2] - t.org[2]; b.z1 = g.own_hi[2] - t.org[2];
-        b.hy_lo = sharded(1) ? r2_[1].lo : 0; b.hy_hi = sharded(1) ? r2_[1].hi : 0;
-        b.hz_lo = sharded(2) ? r2_[2].lo : 0; b.hz_hi = sharded(2) ? r2_[2].hi : 0;
-        do_exchange(1, b);
-    });
+    conv_->set_mid_exchange([this](cpx* work, const TileGeom& t) { do_exchange(1, spectrum_box(work, t)); });
 }
 
 void Engine::exchange_halos() {

@@ -156,16 +156,32 @@ typedef int (*ExchangeFn)(void* user, int which, const HaloBox* box);      // ho
 
 class HaloComm {
   public:
-    HaloComm(std::shared_ptr<NcclComm> comm, int py, int pz, stream_t s);
+    // collective over the communicator.  need_y / need_z: floats this rank pushes per y / z neighbour and exchange at most.
+    HaloComm(std::shared_ptr<NcclComm> comm, int py, int pz, stream_t s, size_t need_y, size_t need_z);
     ~HaloComm();
     void exchange(const HaloBox& b);     // enqueued on the stream; the host does not block
+    int transport() const { return peer_ ? 1 : 0; }      // 0: NCCL send/recv, 1: direct stores into the neighbours' memory
   private:
     void reserve(size_t floats);
+    void exchange_nccl(const HaloBox& b);
+    void exchange_peer(const HaloBox& b);
+    void setup_peer(size_t need_y, size_t need_z);
+    void close_peer();
     std::shared_ptr<NcclComm> comm_;
     int py_, pz_, ry_ = 0, rz_ = 0;
     stream_t stream_;
     size_t stage_floats_ = 0;
     float* stage_[4] = {nullptr, nullptr, nullptr, nullptr};
+    // peer transport: one region per rank = 8 landing buffers ({from lower y, from upper y, from lower z, from upper z} x parity)
+    // + 4 arrival counters, mapped into the neighbours with CUDA IPC (or used directly when the neighbour lives in this process)
+    bool peer_ = false;
+    size_t cap_y_ = 0, cap_z_ = 0;
+    float* region_ = nullptr;
+    float* nb_region_[4] = {nullptr, nullptr, nullptr, nullptr};     // neighbour regions: lower y, upper y, lower z, upper z
+    bool nb_ipc_[4] = {false, false, false, false};
+    unsigned seq_ = 0;
+    float* landing(float* region, int src, int parity) const;
+    unsigned* flags(float* region) const;
 };
 
 // ---- point-wise device stages (pointwise.cpp) -------------------------------------------------------------------------
@@ -237,6 +253,7 @@ class Engine {
     // host-provided exchange instead of NCCL (the stream is synchronised before every call; see mvd_set_exchange_callback)
     void set_exchange_callback(ExchangeFn fn, void* user) { host_exchange_ = fn; host_exchange_user_ = user; install_mid_exchange(); }
     void exchange_halos();
+    int exchange_transport() const { return host_exchange_ ? 2 : (comm_ ? comm_->transport() : -1); }
     void view_update(int v);                               // asynchronous on the engine stream
     void fetch_stats(int count, IterStats* out);           // last `count` view updates (synchronises)
     void run_iterations(int n, IterStats* out /* n*V or null */);
@@ -292,6 +309,9 @@ class Engine {
     bool has_exchange() const { return comm_ != nullptr || host_exchange_ != nullptr; }
     void do_exchange(int which, const HaloBox& b);
     void exchange_psi(float* psi);
+    HaloBox psi_box(float* psi) const;
+    HaloBox spectrum_box(cpx* work, const TileGeom& t) const;
+
     void install_mid_exchange();
     std::vector<float*> integral_;  // Mul iteration: one integral volume per view
     double* lut_dev_ = nullptr;     // cosine blending LUT

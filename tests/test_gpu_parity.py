@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "small_case.npz")
 EPS32 = 1.5e-7
 
@@ -463,3 +464,62 @@ def test_in_library_halo_exchange_two_gpus(product_lib, oracle, axis, scheme):
         else:
             full[:, lo:hi] = part
     assert oracle.rel_l2(full, psi64) <= rel_tol(2)
+
+
+def _two_process_worker(rank, world, port, out_dir, axis, scheme, transport):
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["MVD_EXCHANGE"] = transport
+    import torch
+    import torch.distributed as dist
+    import mvdecon_oracle as o
+    import mvrecon_b200 as m
+    from mvrecon_b200 import sharding
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)       # plumbing for the unique id only
+    lib = m.lib()
+    dims = (48, 40, 36)
+    ds = o.make_synthetic(dims, 2, seed=5, psf_size_xyz=(5, 7, 5), psf_sigma_xyz=(1.0, 1.4, 1.2), bead_density=1024)
+    views, psi0, avg = o.make_oracle_views(ds, o.EFFICIENT_BAYESIAN)
+    n = dims[0] if axis == "z" else dims[1]
+    H = (3 if scheme == 1 else 6) if axis == "y" else (2 if scheme == 1 else 4)
+    lo, hi = sharding.slab_range(n, world, rank)
+    a0, a1 = sharding.extended_range(lo, hi, n, H)
+    sl = (slice(a0, a1),) if axis == "z" else (slice(None), slice(a0, a1))
+    loc = [m.DeconView(np.ascontiguousarray(ds.images[v][sl]), np.ascontiguousarray(ds.weights[v][sl]), ds.psfs[v],
+                       m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(2)]
+    kw = {"shard": (lo, hi, a0, a1 - a0)} if axis == "z" else {"shard_y": (lo, hi, a0, a1 - a0)}
+    d = m.DeconViews(loc, global_dims_zyx=dims, device=rank, exchange_scheme=scheme, **kw)
+    ids = [lib.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    comm = lib.comm_create(ids[0], world, rank, rank)
+    d.comm_attach(comm, *((1, world) if axis == "z" else (world, 1)))
+    assert d.exchange_transport() == ("peer-stores" if transport == "peer" else "nccl")
+    dec = m.MultiViewDeconvolutionSeq(d, 3, m.PsiInitFromRAI(np.ascontiguousarray(psi0[sl]), [v.max_intensity for v in views]))
+    dec.runIterations()
+    own = (slice(lo - a0, hi - a0),) if axis == "z" else (slice(None), slice(lo - a0, hi - a0))
+    np.save(os.path.join(out_dir, f"part{rank}.npy"), dec.getPSI()[own])
+    d.close()
+    comm.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("axis,scheme,transport", [("y", 1, "peer"), ("z", 1, "peer"), ("z", 0, "peer"), ("y", 1, "nccl")])
+def test_two_processes_two_gpus(product_lib, oracle, tmp_path, axis, scheme, transport):
+    """one process per GPU (the bench.py / production layout): halos stored straight into the neighbour's HBM through CUDA IPC
+    mappings, or sent with NCCL; three iterations must equal the whole-volume oracle"""
+    if product_lib.getNumDevicesCUDA() < 2:
+        pytest.skip("needs two devices")
+    import torch.multiprocessing as mp
+    port = 32500 + (os.getpid() % 2000) + 11 * scheme + (5 if axis == "y" else 0) + (23 if transport == "nccl" else 0)
+    mp.start_processes(_two_process_worker, args=(2, port, str(tmp_path), axis, scheme, transport), nprocs=2, join=True, start_method="spawn")
+    ds = oracle.make_synthetic((48, 40, 36), 2, seed=5, psf_size_xyz=(5, 7, 5), psf_sigma_xyz=(1.0, 1.4, 1.2), bead_density=1024)
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN)
+    ref, _ = oracle.run_iterations_seq(psi0, views, 3, 0.0, dtype=np.float64)
+    got = np.concatenate([np.load(tmp_path / f"part{r}.npy") for r in range(2)], axis=0 if axis == "z" else 1)
+    assert oracle.rel_l2(got, ref) <= rel_tol(3)
