@@ -371,6 +371,22 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    if os.environ.get("BENCH_EXCHANGE_ONLY") and use_lib_comm:          # development: cost of the bare psi halo exchange
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(5):
+            dv.exchange_halos()
+        dv.synchronize(); dist.barrier()
+        ea.record(stream)
+        for _ in range(50):
+            dv.exchange_halos()
+        eb.record(stream); eb.synchronize()
+        t = torch.tensor([ea.elapsed_time(eb) / 50 * 1e3], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(json.dumps({"exchange_only_us": float(t.item()), "transport": transport, "grid": [py, pz], "halo": [Hy, Hz],
+                              "local_box_zyx": [z1 - z0, y1 - y0, nx]}))
+        dv.close(); dist.barrier(); dist.destroy_process_group()
+        return
     dv.set_profiling(True)
     dv.pass_times(reset=True)
     sampler = ClockSampler(local)

@@ -34,8 +34,11 @@ struct NcclApi {
 NcclApi& nccl() {
     static NcclApi api;
     if (api.handle) return api;
+    // an NCCL the process already holds (e.g. the one bundled with torch) wins; MVD_NCCL_LIB names a specific file
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* n : names) { api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+    for (const char* n : names) { api.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD); if (api.handle) break; }
+    if (!api.handle) if (const char* e = std::getenv("MVD_NCCL_LIB")) api.handle = dlopen(e, RTLD_NOW | RTLD_LOCAL);
+    for (const char* n : names) { if (api.handle) break; api.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL); }
     if (!api.handle) throw Error("NCCL is not available (dlopen libnccl.so.2 failed): multi-GPU halo exchange needs it");
 #define MVD_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, name)); if (!api.field) throw Error("NCCL symbol missing: " name);
     MVD_SYM(GetUniqueId, "ncclGetUniqueId") MVD_SYM(CommInitRank, "ncclCommInitRank") MVD_SYM(CommDestroy, "ncclCommDestroy")

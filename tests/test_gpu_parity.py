@@ -415,6 +415,7 @@ def test_in_library_halo_exchange_two_gpus(product_lib, oracle, axis, scheme):
     if product_lib.getNumDevicesCUDA() < 2:
         pytest.skip("needs two devices")
     import threading
+    import torch  # noqa: F401  (loads torch's bundled NCCL before the library dlopens one: a process can hold only one libnccl.so.2)
     import mvrecon_b200 as m
     ds = oracle.make_synthetic((48, 40, 36), 2, seed=5, psf_size_xyz=(5, 7, 5), psf_sigma_xyz=(1.0, 1.4, 1.2), bead_density=1024)
     views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN)
