@@ -149,6 +149,39 @@ MVD_API int mvd_make_blending_weights_affine(mvd_context* ctx, int v, const int 
                                              const float blending[3], const double inv_affine[12], const int bbox_offset[3]);
 MVD_API int mvd_normalize_weights(mvd_context* ctx, double osem_speedup, int additional_smooth, float max_diff_range, float scaling_range);
 MVD_API int mvd_get_weight(mvd_context* ctx, int v, float* weight_host);
+MVD_API int mvd_get_image(mvd_context* ctx, int v, float* image_host);      /* download of view v's (possibly generated) image */
+
+/* ---- the step before the loop: view materialisation and PSF preparation -------------------------------------------
+ * mvd_fuse_group = ProcessInputImages.fuseGroups for ONE group (M/process/deconvolution/util/ProcessInputImages.java:307-393): every raw
+ * view (host memory, zero-min, as the ImgLoader delivers it) is resampled into the context's fused grid on the device --
+ * TransformView.transformView (M/process/fusion/transformed/TransformView.java:59-75; TransformedInputRandomAccess.java:60-82): world =
+ * voxel + bbox_min, raw position = inv_affine * world in double, n-linear (1) or nearest (0) sample where strictly inside the raw image,
+ * max(min_value_img, .) there and outside_value elsewhere (reference: MultiViewDeconvolution.minValueImg = 1, outsideValueImg = 0) -- then
+ * image = FusedRandomAccess AVG with the fusion blending weights (FusedRandomAccess.java:66-91), weight = sum of the deconvolution
+ * blending weights (CombineWeightsSumRandomAccess.java:40-51).  Blending border / range must already be adjusted
+ * (FusionTools.adjustBlending); *_blending = 0 means a constant weight of 1.  Result: view v's image and weight, resident on the device
+ * (no fused-size host arrays, no H2D of fused volumes).  Follow with mvd_normalize_weights.                                          */
+typedef struct mvd_raw_view {
+    const float* raw;
+    int dims[3];                 /* (x,y,z) */
+    double inv_affine[12];       /* row-packed inverse of the view -> world AffineTransform3D (after any downsampling adjustment) */
+    int interpolation;           /* 0 nearest neighbour, 1 linear */
+    int fusion_blending; float fusion_border[3], fusion_range[3];
+    int decon_blending;  float decon_border[3], decon_range[3];
+} mvd_raw_view;
+MVD_API int mvd_fuse_group(mvd_context* ctx, int v, const mvd_raw_view* views, int count, const int bbox_min[3], float min_value_img,
+                           float outside_value);
+MVD_API int mvd_last_fuse_group_ms(mvd_context* ctx, double* ms);     /* device time of the last mvd_fuse_group kernel (CUDA events) */
+/* PSFPreparation.loadGroupTransformPSFs (M/process/deconvolution/util/PSFPreparation.java:41-89), host side (PSFs are tiny):
+ * mvd_psf_transformed_dims / mvd_psf_transform = PSFExtraction.getTransformedNormalizedPSF (M/process/psf/PSFExtraction.java:182-193,
+ * 367-451, 453-473): min-max normalisation, then n-linear resampling of the zero-extended PSF so that the centre stays the centre and all
+ * sizes are odd; affine / inv_affine = the view's model and its inverse, row-packed.  mvd_psf_average = PSFCombination.computeAverageImage
+ * (M/process/psf/PSFCombination.java:74-135; dims = count x 3 ints; out may be NULL to query out_dims).  mvd_psf_make_same_size =
+ * PSFCombination.makeSameSize (:182-212).  The results feed mvd_set_psf.                                                              */
+MVD_API int mvd_psf_transformed_dims(const int dims[3], const double affine[12], int new_dims[3]);
+MVD_API int mvd_psf_transform(const float* psf, const int dims[3], const double affine[12], const double inv_affine[12], float* out);
+MVD_API int mvd_psf_average(const float* const* psfs, const int* dims, int count, int use_max, int out_dims[3], float* out);
+MVD_API int mvd_psf_make_same_size(const float* psf, const int dims[3], const int new_dims[3], float* out);
 
 /* MultiViewDeconvolutionMul.runNextIteration (M/process/deconvolution/MultiViewDeconvolutionMul.java:116-245,
  * iteration/mul/ComputeBlockMulThreadCPU.java:87-188, mul/DeconvolutionMethods.java:370-419): ONE psi update per iteration from all

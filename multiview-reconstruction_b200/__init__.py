@@ -66,6 +66,13 @@ class HaloBox(C.Structure):
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(HaloBox))
 
 
+class _RawView(C.Structure):
+    """mvd_raw_view"""
+    _fields_ = [("raw", C.POINTER(C.c_float)), ("dims", C.c_int * 3), ("inv_affine", C.c_double * 12), ("interpolation", C.c_int),
+                ("fusion_blending", C.c_int), ("fusion_border", C.c_float * 3), ("fusion_range", C.c_float * 3),
+                ("decon_blending", C.c_int), ("decon_border", C.c_float * 3), ("decon_range", C.c_float * 3)]
+
+
 _F = C.POINTER(C.c_float)
 _I = C.POINTER(C.c_int)
 _D = C.POINTER(C.c_double)
@@ -101,6 +108,7 @@ SYMBOLS = {
     "mvd_make_blending_weights_affine": (C.c_int, [C.c_void_p, C.c_int, _I, _I, _F, _F, _D, _I]),
     "mvd_normalize_weights": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_float, C.c_float]),
     "mvd_get_weight": (C.c_int, [C.c_void_p, C.c_int, _F]),
+    "mvd_get_image": (C.c_int, [C.c_void_p, C.c_int, _F]),
     "mvd_run_iteration_mul": (C.c_int, [C.c_void_p, _D]),
     "mvd_run_view_update": (C.c_int, [C.c_void_p, C.c_int, _D]),
     "mvd_run_iterations": (C.c_int, [C.c_void_p, C.c_int, _D]),
@@ -118,6 +126,12 @@ SYMBOLS = {
     "mvd_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mvd_set_exchange_callback": (C.c_int, [C.c_void_p, EXCHANGE_FN, C.c_void_p]),
     "mvd_exchange_transport": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "mvd_fuse_group": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_RawView), C.c_int, C.POINTER(C.c_int), C.c_float, C.c_float]),
+    "mvd_last_fuse_group_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "mvd_psf_transformed_dims": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "mvd_psf_transform": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+    "mvd_psf_average": (C.c_int, [C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    "mvd_psf_make_same_size": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "mvd_exchange_halos": (C.c_int, [C.c_void_p]),
     "mvd_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "mvd_get_pass_times": (C.c_int, [C.c_void_p, _D, C.POINTER(C.c_longlong), C.c_int]),
@@ -184,6 +198,36 @@ class Lib:
         h = C.c_void_p()
         self.check(self.dll.mvd_comm_create(C.create_string_buffer(bytes(unique_id), 128), int(world), int(rank), int(device), C.byref(h)))
         return Communicator(self, h)
+
+    # ---- PSF preparation (PSFPreparation.loadGroupTransformPSFs, M/process/deconvolution/util/PSFPreparation.java:41-89) ----------
+    def psf_transform(self, psf: np.ndarray, affine, inv_affine) -> np.ndarray:
+        """PSFExtraction.getTransformedNormalizedPSF: affine / inv_affine = row-packed 3x4 model and its inverse"""
+        psf = _f32(psf)
+        a = (C.c_double * 12)(*[float(x) for x in np.asarray(affine, dtype=np.float64).ravel()])
+        ia = (C.c_double * 12)(*[float(x) for x in np.asarray(inv_affine, dtype=np.float64).ravel()])
+        nd = (C.c_int * 3)()
+        self.check(self.dll.mvd_psf_transformed_dims(_i3(_xyz(psf)), a, nd))
+        out = np.empty((nd[2], nd[1], nd[0]), dtype=np.float32)
+        self.check(self.dll.mvd_psf_transform(_fp(psf), _i3(_xyz(psf)), a, ia, _fp(out)))
+        return out
+
+    def psf_average(self, psfs: Sequence[np.ndarray], use_max: bool = False) -> np.ndarray:
+        """PSFCombination.computeAverageImage"""
+        ps = [_f32(p) for p in psfs]
+        ptrs = (C.POINTER(C.c_float) * len(ps))(*[_fp(p) for p in ps])
+        dims = (C.c_int * (3 * len(ps)))(*[d for p in ps for d in _xyz(p)])
+        od = (C.c_int * 3)()
+        self.check(self.dll.mvd_psf_average(ptrs, dims, len(ps), int(use_max), od, None))
+        out = np.empty((od[2], od[1], od[0]), dtype=np.float32)
+        self.check(self.dll.mvd_psf_average(ptrs, dims, len(ps), int(use_max), od, _fp(out)))
+        return out
+
+    def psf_make_same_size(self, psf: np.ndarray, size_zyx: Sequence[int]) -> np.ndarray:
+        """PSFCombination.makeSameSize"""
+        psf = _f32(psf)
+        out = np.empty(tuple(int(x) for x in size_zyx), dtype=np.float32)
+        self.check(self.dll.mvd_psf_make_same_size(_fp(psf), _i3(_xyz(psf)), _i3(_xyz(out)), _fp(out)))
+        return out
 
     def getNumDevicesCUDA(self) -> int:
         return int(self.dll.getNumDevicesCUDA())
@@ -294,12 +338,67 @@ class DeconViewPSF:
         return self._kernel2
 
 
+class RawView:
+    """One raw (untransformed) view of a group as ProcessInputImages.fuseGroups sees it: the ImgLoader's zero-min image, the INVERSE of
+    its (downsampling-adjusted) view -> world model, the interpolation, and the already adjusted blending (border_xyz, range_xyz) for the
+    fusion and the deconvolution weights (None = constant 1)."""
+
+    def __init__(self, raw: np.ndarray, inv_affine, interpolation: int = 1, fusion_blending=None, decon_blending=None):
+        self.raw = _f32(raw)
+        self.inv_affine = np.asarray(inv_affine, dtype=np.float64).ravel()
+        if self.raw.ndim != 3 or self.inv_affine.size != 12:
+            raise MvdError("RawView: 3-d image and a row-packed 3x4 inverse affine")
+        self.interpolation = int(interpolation)
+        self.fusion_blending, self.decon_blending = fusion_blending, decon_blending
+
+
+class FusedGroup:
+    """A virtual view given by its raw views instead of a fused-grid image: materialised on the device by mvd_fuse_group
+    (ProcessInputImages.fuseGroups, M/process/deconvolution/util/ProcessInputImages.java:279-399)."""
+
+    def __init__(self, raw_views: Sequence[RawView], bbox_min_xyz: Sequence[int], dims_zyx: Sequence[int],
+                 min_value_img: float = 1.0, outside_value: float = 0.0):
+        self.raw_views = list(raw_views)
+        self.bbox_min = tuple(int(x) for x in bbox_min_xyz)
+        self.shape = tuple(int(x) for x in dims_zyx)
+        self.ndim = 3
+        self.min_value_img, self.outside_value = float(min_value_img), float(outside_value)
+
+    def _records(self):
+        arr = (_RawView * len(self.raw_views))()
+        for r, rv in zip(arr, self.raw_views):
+            r.raw = _fp(rv.raw)
+            r.dims[0], r.dims[1], r.dims[2] = _xyz(rv.raw)
+            for i in range(12):
+                r.inv_affine[i] = float(rv.inv_affine[i])
+            r.interpolation = rv.interpolation
+            for name, bl in (("fusion", rv.fusion_blending), ("decon", rv.decon_blending)):
+                setattr(r, name + "_blending", 0 if bl is None else 1)
+                if bl is not None:
+                    for d in range(3):
+                        getattr(r, name + "_border")[d] = float(bl[0][d])
+                        getattr(r, name + "_range")[d] = float(bl[1][d])
+        return arr
+
+
+def loadGroupTransformPSFs(groups, sameSizeForAll: bool = True, library: Optional["Lib"] = None) -> List[np.ndarray]:
+    """PSFPreparation.loadGroupTransformPSFs (M/process/deconvolution/util/PSFPreparation.java:41-89).  groups: one list per virtual view of
+    (raw psf, affine, inv_affine) per member view (row-packed 3x4 downsampled model and its inverse).  Every PSF is min-max normalised and
+    resampled, a group's PSFs are averaged over their minimal size, and with sameSizeForAll all results are centred into the largest size."""
+    L = library or lib()
+    out = [L.psf_average([L.psf_transform(p, a, ia) for p, a, ia in g], False) for g in groups]
+    if sameSizeForAll:
+        size = tuple(max(p.shape[d] for p in out) for d in range(3))
+        out = [L.psf_make_same_size(p, size) for p in out]
+    return out
+
+
 class DeconView:
     """M/process/deconvolution/DeconView.java:118-184 -- image, weight, PSF of one virtual view."""
 
     def __init__(self, image: np.ndarray, weight: np.ndarray, kernel: np.ndarray, psfType: PSFTYPE = PSFTYPE.INDEPENDENT,
                  title: Optional[str] = None):
-        self.image = image if isinstance(image, DeviceArray) else _f32(image)
+        self.image = image if isinstance(image, (DeviceArray, FusedGroup)) else _f32(image)
         self.weight = weight if (weight is None or isinstance(weight, DeviceArray)) else _f32(weight)   # None: generated on the device
         if (self.weight is not None and self.image.shape != self.weight.shape) or self.image.ndim != 3:
             raise MvdError("image and weight must be 3-d volumes of identical size")
@@ -357,7 +456,13 @@ class DeconViews:
         self.lib.check(self.lib.dll.mvd_create(C.byref(cfg), C.byref(self._ctx)))
         try:
             for i, v in enumerate(self.views):
-                if isinstance(v.image, DeviceArray) or isinstance(v.weight, DeviceArray):
+                if isinstance(v.image, FusedGroup):                  # raw views -> fused-grid image + summed weight, on the device
+                    if v.weight is not None:
+                        raise MvdError("a FusedGroup view generates its own weight")
+                    g = v.image
+                    self.lib.check(self.lib.dll.mvd_fuse_group(self._ctx, i, g._records(), len(g.raw_views), _i3(g.bbox_min),
+                                                               g.min_value_img, g.outside_value))
+                elif isinstance(v.image, DeviceArray) or isinstance(v.weight, DeviceArray):
                     if not (isinstance(v.image, DeviceArray) and isinstance(v.weight, DeviceArray)):
                         raise MvdError("image and weight of a view must both be host arrays or both DeviceArrays")
                     self.lib.check(self.lib.dll.mvd_set_view_device(self._ctx, i, C.c_void_p(v.image.ptr), C.c_void_p(v.weight.ptr)))
@@ -430,6 +535,16 @@ class DeconViews:
         w = np.empty(self.local_shape, dtype=np.float32)
         self.lib.check(self.lib.dll.mvd_get_weight(self._ctx, int(v), _fp(w)))
         return w
+
+    def last_fuse_group_ms(self) -> float:
+        ms = C.c_double()
+        self.lib.check(self.lib.dll.mvd_last_fuse_group_ms(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def getImage(self, v: int) -> np.ndarray:
+        im = np.empty(self.local_shape, dtype=np.float32)
+        self.lib.check(self.lib.dll.mvd_get_image(self._ctx, int(v), _fp(im)))
+        return im
 
     def psi_device_ptr(self) -> int:
         p = C.c_void_p()

@@ -162,6 +162,9 @@ int mvd_normalize_weights(mvd_context* ctx, double osem_speedup, int additional_
 int mvd_get_weight(mvd_context* ctx, int v, float* out) {
     return guarded([&] { require(ctx && out, "null argument"); ctx->engine->get_weight_host(v, out); });
 }
+int mvd_get_image(mvd_context* ctx, int v, float* out) {
+    return guarded([&] { require(ctx && out, "null argument"); ctx->engine->get_image_host(v, out); });
+}
 int mvd_run_iteration_mul(mvd_context* ctx, double stats[2]) {
     return guarded([&] {
         require(ctx, "null context");
@@ -259,6 +262,54 @@ int mvd_set_exchange_callback(mvd_context* ctx, mvd_exchange_fn fn, void* user) 
     return guarded([&] {
         require(ctx != nullptr, "null argument");
         ctx->engine->set_exchange_callback(reinterpret_cast<ExchangeFn>(fn), user);
+    });
+}
+static_assert(sizeof(mvd_raw_view) == sizeof(RawViewDev), "mvd_raw_view mirrors RawViewDev");
+int mvd_fuse_group(mvd_context* ctx, int v, const mvd_raw_view* views, int count, const int bbox_min[3], float min_value_img,
+                   float outside_value) {
+    return guarded([&] {
+        require(ctx && views && bbox_min, "null argument");
+        ctx->engine->fuse_group_host(v, reinterpret_cast<const RawViewDev*>(views), count, bbox_min, min_value_img, outside_value);
+    });
+}
+int mvd_last_fuse_group_ms(mvd_context* ctx, double* ms) {
+    return guarded([&] { require(ctx && ms, "null argument"); *ms = ctx->engine->last_fuse_group_ms(); });
+}
+int mvd_psf_transformed_dims(const int dims[3], const double affine[12], int new_dims[3]) {
+    return guarded([&] {
+        require(dims && affine && new_dims, "null argument");
+        double off[3];
+        psf_transformed_geometry(dims, affine, new_dims, off);
+    });
+}
+int mvd_psf_transform(const float* psf, const int dims[3], const double affine[12], const double inv_affine[12], float* out) {
+    return guarded([&] {
+        require(psf && dims && affine && inv_affine && out, "null argument");
+        require(dims[0] > 0 && dims[1] > 0 && dims[2] > 0, "empty PSF");
+        int nd[3];
+        const std::vector<float> r = psf_transform_normalized(psf, dims, affine, inv_affine, nd);
+        std::copy(r.begin(), r.end(), out);
+    });
+}
+int mvd_psf_average(const float* const* psfs, const int* dims, int count, int use_max, int out_dims[3], float* out) {
+    return guarded([&] {
+        require(psfs && dims && out_dims && count > 0, "null argument");
+        if (!out) {
+            for (int d = 0; d < 3; ++d) {
+                out_dims[d] = dims[d];
+                for (int j = 1; j < count; ++j) out_dims[d] = use_max ? std::max(out_dims[d], dims[3 * j + d]) : std::min(out_dims[d], dims[3 * j + d]);
+            }
+            return;
+        }
+        const std::vector<float> r = psf_average(psfs, reinterpret_cast<const int(*)[3]>(dims), count, use_max != 0, out_dims);
+        std::copy(r.begin(), r.end(), out);
+    });
+}
+int mvd_psf_make_same_size(const float* psf, const int dims[3], const int new_dims[3], float* out) {
+    return guarded([&] {
+        require(psf && dims && new_dims && out, "null argument");
+        const std::vector<float> r = psf_make_same_size(psf, dims, new_dims);
+        std::copy(r.begin(), r.end(), out);
     });
 }
 int mvd_exchange_transport(mvd_context* ctx, int* transport) {

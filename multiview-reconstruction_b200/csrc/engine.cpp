@@ -119,11 +119,19 @@ struct FillParts {      // unused partial-statistics slots must read as {0, -1}
     double* ps; float* pm;
     MVD_HD void operator()(long long i) const { ps[i] = 0.0; pm[i] = -1.f; }
 };
+// Deterministic two-level reduction: lane l adds the partials l, l + 256, ... in index order, then one thread adds the 256 lane sums in
+// order.  The loads are issued in batches of 8 ahead of the (ordered) additions so the single CTA is not bound by one L2 latency per term.
 struct ReduceParts1 {
     const double* ps; const float* pm; int n; double* ts; float* tm;
     MVD_HD void operator()(long long lane) const {
         double s = 0.0; float m = -1.f;
-        for (int i = (int)lane; i < n; i += 256) { s += ps[i]; m = pm[i] > m ? pm[i] : m; }
+        int i = (int)lane;
+        for (; i + 7 * 256 < n; i += 8 * 256) {
+            double a[8]; float b[8];
+            for (int k = 0; k < 8; ++k) { a[k] = ps[i + k * 256]; b[k] = pm[i + k * 256]; }
+            for (int k = 0; k < 8; ++k) { s += a[k]; m = b[k] > m ? b[k] : m; }
+        }
+        for (; i < n; i += 256) { s += ps[i]; m = pm[i] > m ? pm[i] : m; }
         ts[lane] = s; tm[lane] = m;
     }
 };
@@ -131,7 +139,11 @@ struct ReduceParts2 {
     const double* ts; const float* tm; double* out;
     MVD_HD void operator()(long long) const {
         double s = 0.0; float m = -1.f;
-        for (int i = 0; i < 256; ++i) { s += ts[i]; m = tm[i] > m ? tm[i] : m; }
+        for (int i = 0; i < 256; i += 16) {
+            double a[16]; float b[16];
+            for (int k = 0; k < 16; ++k) { a[k] = ts[i + k]; b[k] = tm[i + k]; }
+            for (int k = 0; k < 16; ++k) { s += a[k]; m = b[k] > m ? b[k] : m; }
+        }
         out[0] = s; out[1] = (double)m;
     }
 };
@@ -764,6 +776,62 @@ void Engine::make_blending_weights(int v, const int box_min[3], const int box_ma
     blend_weights(stream_, vw.weight_owned, lut_dev_, cfg_.geom.vol, cfg_.geom.goff, box_min, box_max, border, blending, inv_affine, bbox_offset);
 }
 
+void Engine::fuse_group_host(int v, const RawViewDev* views_host, int count, const int bbox_min[3], float min_value_img, float outside_value) {
+    if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
+    if (count < 1 || count > 64) throw Error("a group needs 1..64 views");
+    dev::set_device(cfg_.device);
+    View& vw = views_[v];
+    if ((vw.img && !vw.img_owned) || (vw.weight && !vw.weight_owned)) throw Error("this view borrows device memory; cannot generate into it");
+    const size_t bytes = sizeof(float) * local_voxels();
+    if (!vw.img_owned) vw.img_owned = (float*)dev::alloc(bytes);
+    if (!vw.weight_owned) vw.weight_owned = (float*)dev::alloc(bytes);
+    if (!lut_dev_) {
+        const std::vector<double> lut = blend_lut();
+        lut_dev_ = (double*)dev::alloc(sizeof(double) * lut.size());
+        dev::h2d(lut_dev_, lut.data(), sizeof(double) * lut.size(), stream_);
+    }
+    std::vector<RawViewDev> hv(views_host, views_host + count);
+    std::vector<float*> raws;
+    RawViewDev* dv = nullptr;
+    try {
+        for (RawViewDev& r : hv) {
+            for (int d = 0; d < 3; ++d) if (r.dims[d] < 2) throw Error("raw views need at least 2 samples per axis");
+            if (!r.raw) throw Error("null raw view");
+            const size_t n = (size_t)r.dims[0] * r.dims[1] * r.dims[2];
+            float* p = (float*)dev::alloc(sizeof(float) * n);
+            raws.push_back(p);
+            dev::h2d(p, r.raw, sizeof(float) * n, stream_);
+            r.raw = p;
+        }
+        dv = (RawViewDev*)dev::alloc(sizeof(RawViewDev) * hv.size());
+        dev::h2d(dv, hv.data(), sizeof(RawViewDev) * hv.size(), stream_);
+#ifndef MVD_HOST_EMU
+        cudaEvent_t e0, e1;
+        MVD_CUDA_CHECK(cudaEventCreate(&e0)); MVD_CUDA_CHECK(cudaEventCreate(&e1));
+        MVD_CUDA_CHECK(cudaEventRecord(e0, stream_));
+#endif
+        fuse_group(stream_, dv, count, vw.img_owned, vw.weight_owned, lut_dev_, cfg_.geom.vol, cfg_.geom.goff, bbox_min, min_value_img, outside_value);
+#ifndef MVD_HOST_EMU
+        MVD_CUDA_CHECK(cudaEventRecord(e1, stream_));
+#endif
+        dev::sync(stream_);
+#ifndef MVD_HOST_EMU
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        last_fuse_ms_ = ms;
+#endif
+    } catch (...) {
+        for (float* p : raws) dev::free_(p);
+        dev::free_(dv);
+        throw;
+    }
+    for (float* p : raws) dev::free_(p);
+    dev::free_(dv);
+    vw.img = vw.img_owned;
+    vw.weight = vw.weight_owned;
+}
+
 void Engine::normalize_view_weights(double osem_speedup, bool additional_smooth, float max_diff_range, float scaling_range) {
     dev::set_device(cfg_.device);
     const int V = cfg_.num_views;
@@ -776,6 +844,14 @@ void Engine::normalize_view_weights(double osem_speedup, bool additional_smooth,
     normalize_weights(stream_, w, V, (long long)local_voxels(), osem_speedup, additional_smooth, max_diff_range, scaling_range);
 }
 
+void Engine::get_image_host(int v, float* out) {
+    if (v < 0 || v >= cfg_.num_views || !views_[v].img) throw Error("no such image");
+    dev::set_device(cfg_.device);
+    View& vw = views_[v];
+    if (vw.pending) { dev::stream_wait(stream_, vw.ready); vw.pending = false; }
+    dev::d2h(out, vw.img, sizeof(float) * local_voxels(), stream_);
+    dev::sync(stream_);
+}
 void Engine::get_weight_host(int v, float* out) {
     if (v < 0 || v >= cfg_.num_views || !views_[v].weight) throw Error("no such weight");
     dev::set_device(cfg_.device);

@@ -195,6 +195,21 @@ void slice_stats(stream_t s, const float* img, int nx, long long nyz, double* ac
 void blend_weights(stream_t s, float* out, const double* lut_dev, const int vol[3], const int goff[3], const int box_min[3], const int box_max[3],
                    const float border[3], const float blending[3], const double* inv_affine = nullptr, const int* bbox_offset = nullptr);
 std::vector<double> blend_lut();
+// one raw (untransformed) view of a group, resident on the device (pointwise.cpp: FuseGroupKernel)
+struct RawViewDev {
+    const float* raw; int dims[3];
+    double im[12];                       // row-packed inverse of the view -> world model
+    int interpolation;                   // 0 nearest neighbour, 1 n-linear
+    int fusion_blend; float fusion_border[3], fusion_range[3];
+    int decon_blend; float decon_border[3], decon_range[3];
+};
+void fuse_group(stream_t s, const RawViewDev* views_dev, int count, float* img_out, float* w_out, const double* lut_dev, const int vol[3],
+                const int goff[3], const int bbox_min[3], float min_value, float outside_value);
+// PSF preparation on the host (kernels are a few thousand voxels; psf_prep.cpp)
+void psf_transformed_geometry(const int dims[3], const double affine[12], int new_dims[3], double offset[3]);
+std::vector<float> psf_transform_normalized(const float* psf, const int dims[3], const double affine[12], const double inv_affine[12], int new_dims[3]);
+std::vector<float> psf_average(const float* const* psfs, const int (*dims)[3], int count, bool use_max, int out_dims[3]);
+std::vector<float> psf_make_same_size(const float* psf, const int dims[3], const int new_dims[3]);
 void normalize_weights(stream_t s, const WeightPtrs& w, int V, long long n, double osem, bool smooth, float max_diff_range, float scaling_range);
 void mul_combine(stream_t st, const MulPtrs& p, int V, const float* psi_in, float* psi_out, long long n, long long own0, long long own1, float lambda,
                  float min_value, float max_intensity, double* stats_dev, float* scratch_max_dev);
@@ -245,7 +260,12 @@ class Engine {
     void make_blending_weights(int v, const int box_min[3], const int box_max[3], const float border[3], const float blending[3],
                                const double* inv_affine = nullptr, const int* bbox_offset = nullptr);
     void normalize_view_weights(double osem_speedup, bool additional_smooth, float max_diff_range, float scaling_range);
+    // ProcessInputImages.fuseGroups for one group: raw host views -> view v's image and (summed) deconvolution weight on the device
+    void fuse_group_host(int v, const RawViewDev* views_host /* raw = host pointers */, int count, const int bbox_min[3], float min_value_img,
+                         float outside_value);
     void get_weight_host(int v, float* out);
+    void get_image_host(int v, float* out);
+    double last_fuse_group_ms() const { return last_fuse_ms_; }      // device time of the last fuse_group kernel (CUDA events)
     // MultiViewDeconvolutionMul.runNextIteration: one psi update from all views (geometric mean of the integrals)
     void iteration_mul();
     // attach the NCCL halo exchange: afterwards every view update / Mul iteration is followed by the exchange of the new psi
@@ -302,6 +322,7 @@ class Engine {
     double* stats_dev_ = nullptr;   // ring of {sum,max} pairs
     void ensure_stats_slot();
     std::unique_ptr<HaloComm> comm_;
+    double last_fuse_ms_ = 0.0;
     ExchangeFn host_exchange_ = nullptr;
     void* host_exchange_user_ = nullptr;
     Reach r1_[3] = {{0, 0}, {0, 0}, {0, 0}}, r2_[3] = {{0, 0}, {0, 0}, {0, 0}};     // kernel reaches (max over views)

@@ -208,6 +208,98 @@ std::vector<double> blend_lut() {      // BlendingRealRandomAccess.java:47-56, i
     return lut;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// View materialisation: ProcessInputImages.fuseGroups for one group on the device
+// (M/process/deconvolution/util/ProcessInputImages.java:307-393).  Per fused voxel and raw view: world = voxel + bbox min,
+// t = inverse affine (double, left to right; TransformedInputRandomAccess.java:63-69); image sample = n-linear / nearest of
+// the raw view where t is strictly inside (AbstractTransformedIntervalRandomAccess.java:73-84), max(minValue, .)
+// (AbstractTransformedImgRandomAccess.java:76-91), else the outside value; FusedRandomAccess AVG with the fusion blending
+// weights (FusedRandomAccess.java:66-91) -> image, CombineWeightsSumRandomAccess of the deconvolution blending weights
+// (weightcombination/CombineWeightsSumRandomAccess.java:40-51) -> weight.  The samplers restate imglib2 8.0.0's
+// NLinearInterpolator3D / NearestNeighborInterpolator for FloatType (see oracle/mvdecon_oracle.py, same section).
+// ---------------------------------------------------------------------------------------------------------------------
+MVD_HD float blend_weight_at(const float loc[3], const int dim_minus1[3], const float border[3], const float blending[3], const double* lut) {
+    float tmp[3];
+    for (int d = 0; d < 3; ++d) {                     // image interval min is 0 (views from the ImgLoader are zero-min)
+        const float l = f_sub(loc[d], 0.f);
+        const float a = f_sub(l, border[d]);
+        const float b = f_sub(f_sub((float)dim_minus1[d], l), border[d]);
+        tmp[d] = a < b ? a : b;
+        if (tmp[d] <= 0.f) return 0.f;
+    }
+    float min_distance = 1.f;
+    for (int d = 0; d < 3; ++d) {
+        const float rel = f_div(tmp[d], blending[d]);
+        if (rel < 1.f) min_distance = (float)((double)min_distance * lut[(int)((double)rel * 1000.0 + 0.5)]);
+    }
+    return min_distance;
+}
+
+MVD_HD float nlinear3_at(const float* raw, const int dims[3], double t0, double t1, double t2) {
+    const double f0 = floor(t0), f1 = floor(t1), f2 = floor(t2);
+    const double w0 = t0 - f0, w1 = t1 - f1, w2 = t2 - f2;
+    const double w0i = 1.0 - w0, w1i = 1.0 - w1, w2i = 1.0 - w2;
+    const long long x = (long long)f0, y = (long long)f1, z = (long long)f2;
+    const long long sy = dims[0], sz = (long long)dims[0] * dims[1];
+    const float* p = raw + z * sz + y * sy + x;
+    // Gray-code corner order of NLinearInterpolator3D; every product is rounded to float (FloatType.mul(double)) before the float add
+    float acc = (float)d_mul((double)p[0], d_mul(d_mul(w0i, w1i), w2i));
+    acc = f_add(acc, (float)d_mul((double)p[1], d_mul(d_mul(w0, w1i), w2i)));
+    acc = f_add(acc, (float)d_mul((double)p[1 + sy], d_mul(d_mul(w0, w1), w2i)));
+    acc = f_add(acc, (float)d_mul((double)p[sy], d_mul(d_mul(w0i, w1), w2i)));
+    acc = f_add(acc, (float)d_mul((double)p[sy + sz], d_mul(d_mul(w0i, w1), w2)));
+    acc = f_add(acc, (float)d_mul((double)p[1 + sy + sz], d_mul(d_mul(w0, w1), w2)));
+    acc = f_add(acc, (float)d_mul((double)p[1 + sz], d_mul(d_mul(w0, w1i), w2)));
+    acc = f_add(acc, (float)d_mul((double)p[sz], d_mul(d_mul(w0i, w1i), w2)));
+    return acc;
+}
+
+struct FuseGroupKernel {
+    const RawViewDev* views; int count;
+    float* img_out; float* w_out; const double* lut;
+    int nx, ny; int goff[3]; int bbox_min[3];
+    float min_value, outside_value;
+    MVD_HD void operator()(long long i) const {
+        const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((long long)nx * ny));
+        const double s0 = (double)((long long)x + goff[0] + bbox_min[0]), s1 = (double)((long long)y + goff[1] + bbox_min[1]),
+                     s2 = (double)((long long)z + goff[2] + bbox_min[2]);
+        double sum_i = 0, sum_w = 0, sum_d = 0;
+        for (int j = 0; j < count; ++j) {
+            const RawViewDev& v = views[j];
+            double t[3];
+            for (int r = 0; r < 3; ++r)
+                t[r] = d_add(d_add(d_add(d_mul(s0, v.im[4 * r]), d_mul(s1, v.im[4 * r + 1])), d_mul(s2, v.im[4 * r + 2])), v.im[4 * r + 3]);
+            float val = outside_value;
+            if (t[0] > 0 && t[1] > 0 && t[2] > 0 && t[0] < (double)(v.dims[0] - 1) && t[1] < (double)(v.dims[1] - 1) && t[2] < (double)(v.dims[2] - 1)) {
+                float smp;
+                if (v.interpolation == 1) smp = nlinear3_at(v.raw, v.dims, t[0], t[1], t[2]);
+                else {                                  // Util.roundToLong: half away from zero (t > 0 here)
+                    const long long rx = (long long)(t[0] + 0.5), ry = (long long)(t[1] + 0.5), rz = (long long)(t[2] + 0.5);
+                    smp = v.raw[(rz * v.dims[1] + ry) * v.dims[0] + rx];
+                }
+                val = smp > min_value ? smp : min_value;                                   // Math.max(minValue, sample)
+            }
+            const float loc[3] = {(float)t[0], (float)t[1], (float)t[2]};                     // TransformedRasteredRandomAccess.java:96-114
+            const int dm1[3] = {v.dims[0] - 1, v.dims[1] - 1, v.dims[2] - 1};
+            const float wf = v.fusion_blend ? blend_weight_at(loc, dm1, v.fusion_border, v.fusion_range, lut) : 1.f;
+            const float wd = v.decon_blend ? blend_weight_at(loc, dm1, v.decon_border, v.decon_range, lut) : 1.f;
+            if (wf != 0.f) { sum_i = d_add(sum_i, d_mul((double)val, (double)wf)); sum_w = d_add(sum_w, (double)wf); }
+            sum_d = d_add(sum_d, (double)wd);
+        }
+        img_out[i] = sum_w > 0 ? (float)(sum_i / sum_w) : 0.f;
+        w_out[i] = (float)sum_d;
+    }
+};
+void fuse_group(stream_t s, const RawViewDev* views_dev, int count, float* img_out, float* w_out, const double* lut_dev, const int vol[3],
+                const int goff[3], const int bbox_min[3], float min_value, float outside_value) {
+    FuseGroupKernel k;
+    k.views = views_dev; k.count = count; k.img_out = img_out; k.w_out = w_out; k.lut = lut_dev;
+    k.nx = vol[0]; k.ny = vol[1];
+    for (int d = 0; d < 3; ++d) { k.goff[d] = goff[d]; k.bbox_min[d] = bbox_min[d]; }
+    k.min_value = min_value; k.outside_value = outside_value;
+    pfor((long long)vol[0] * vol[1] * vol[2], k, s);
+}
+
 // NormalizingRandomAccess.get for every view, in place (normalization/NormalizingRandomAccess.java:75-109,183-214)
 struct NormalizeWeights {
     WeightPtrs w; int V; double osem; int smooth; float max_diff_range, scaling_range;

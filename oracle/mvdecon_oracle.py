@@ -671,6 +671,170 @@ def blending_weight_affine(dims_zyx: Sequence[int], bbox_offset_xyz: Sequence[in
     return w
 
 
+# -----------------------------------------------------------------------------------------------------------------------
+# Input view materialisation: TransformView + FusedRandomAccess(AVG) + CombineWeights(SUM) of one group,
+# ProcessInputImages.fuseGroups (M/process/deconvolution/util/ProcessInputImages.java:279-399).
+# The n-linear / nearest-neighbour samplers live in imglib2 8.0.0 (pom.xml:110), which is not in /root/reference: restated from
+# its published NLinearInterpolator3D (Gray-code corner order 000,100,110,010,011,111,101,001; every corner value is
+# multiplied by its double weight product and rounded to float -- FloatType.mul(double) -- then added in float) and
+# NearestNeighborInterpolator (Round: half away from zero; positions are positive here).  PARITY UNPINNED like the rest.
+# -----------------------------------------------------------------------------------------------------------------------
+def _world_to_raw(dims_zyx, bbox_min_xyz, inv_affine_row_packed):
+    """s = position + offset (TransformedInputRandomAccess.java:63-66), t = applyInverse(s): double, left to right (:69)."""
+    nz, ny, nx = dims_zyx
+    im = np.asarray(inv_affine_row_packed, dtype=np.float64).ravel()
+    s2, s1, s0 = np.meshgrid(np.arange(nz, dtype=np.float64) + bbox_min_xyz[2], np.arange(ny, dtype=np.float64) + bbox_min_xyz[1],
+                             np.arange(nx, dtype=np.float64) + bbox_min_xyz[0], indexing="ij")
+    return [((s0 * im[4 * r] + s1 * im[4 * r + 1]) + s2 * im[4 * r + 2]) + im[4 * r + 3] for r in range(3)]
+
+
+def nlinear3(raw: np.ndarray, t: Sequence[np.ndarray], extend_zero: bool = False) -> np.ndarray:
+    """imglib2 NLinearInterpolator3D.get() for FloatType at real positions t = [tx, ty, tz] (see the section header).
+    extend_zero: Views.extendZero (PSFExtraction.transform) instead of requiring the 8 corners inside."""
+    f32, f64 = np.float32, np.float64
+    rz, ry, rx = raw.shape
+    fl = [np.floor(c) for c in t]
+    w = [c - f for c, f in zip(t, fl)]
+    wi = [1.0 - a for a in w]
+    base = [f.astype(np.int64) for f in fl]
+
+    def corner(dx, dy, dz):
+        x, y, z = base[0] + dx, base[1] + dy, base[2] + dz
+        ok = (x >= 0) & (x < rx) & (y >= 0) & (y < ry) & (z >= 0) & (z < rz)
+        v = raw[np.clip(z, 0, rz - 1), np.clip(y, 0, ry - 1), np.clip(x, 0, rx - 1)].astype(f32)
+        return np.where(ok, v, f32(0)) if extend_zero else v
+
+    def term(dx, dy, dz):
+        wx = w[0] if dx else wi[0]
+        wy = w[1] if dy else wi[1]
+        wz = w[2] if dz else wi[2]
+        return (corner(dx, dy, dz).astype(f64) * ((wx * wy) * wz)).astype(f32)
+
+    acc = term(0, 0, 0)
+    for c in ((1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 1, 1), (1, 1, 1), (1, 0, 1), (0, 0, 1)):
+        acc = (acc + term(*c)).astype(f32)
+    return acc
+
+
+def transform_view(raw: np.ndarray, inv_affine_row_packed, bbox_min_xyz, dims_zyx, interpolation: int = 1, has_min_value: bool = True,
+                   min_value: float = MIN_VALUE_IMG, outside_value: float = OUTSIDE_VALUE_IMG) -> np.ndarray:
+    """TransformView.transformView (M/process/fusion/transformed/TransformView.java:59-75) evaluated on the whole bounding box:
+    TransformedInputRandomAccess.get (:60-82) with the strict inside test of AbstractTransformedIntervalRandomAccess.java:73-84 and
+    getInsideValue = max(minValue, sample) (AbstractTransformedImgRandomAccess.java:76-91)."""
+    f32 = np.float32
+    raw = np.asarray(raw, dtype=f32)
+    rz, ry, rx = raw.shape
+    t = _world_to_raw(dims_zyx, bbox_min_xyz, inv_affine_row_packed)
+    inside = (t[0] > 0) & (t[1] > 0) & (t[2] > 0) & (t[0] < rx - 1) & (t[1] < ry - 1) & (t[2] < rz - 1)
+    tc = [np.where(inside, c, 0.25) for c in t]                     # any valid position for the masked-out voxels
+    if interpolation == 1:
+        val = nlinear3(raw, tc)
+    else:
+        idx = [np.trunc(c + 0.5 * np.sign(c)).astype(np.int64) for c in tc]       # Util.roundToLong
+        val = raw[np.clip(idx[2], 0, rz - 1), np.clip(idx[1], 0, ry - 1), np.clip(idx[0], 0, rx - 1)]
+    if has_min_value:
+        val = np.maximum(f32(min_value), val)
+    return np.where(inside, val, f32(outside_value)).astype(f32)
+
+
+def fuse_group(raws: Sequence[np.ndarray], inv_affines, bbox_min_xyz, dims_zyx, interpolation: int = 1,
+               fusion_blending=None, decon_blending=None, min_value: float = MIN_VALUE_IMG, outside_value: float = OUTSIDE_VALUE_IMG):
+    """ProcessInputImages.fuseGroups for ONE group (ProcessInputImages.java:307-393): image = FusedRandomAccess AVG
+    (M/process/fusion/transformed/FusedRandomAccess.java:66-91: views with weight 0 are skipped, sums in double, 0 where nothing
+    contributes) of the transformed views with the fusion blending weights (or 1), weight = CombineWeightsSumRandomAccess
+    (weightcombination/CombineWeightsSumRandomAccess.java:40-51) of the deconvolution blending weights (or 1).
+    *_blending: None or a list of (border_xyz, range_xyz) per view, already adjusted (FusionTools.adjustBlending)."""
+    f32, f64 = np.float32, np.float64
+    sum_i = np.zeros(dims_zyx, dtype=f64)
+    sum_w = np.zeros(dims_zyx, dtype=f64)
+    sum_d = np.zeros(dims_zyx, dtype=f64)
+    for j, (raw, ia) in enumerate(zip(raws, inv_affines)):
+        img = transform_view(raw, ia, bbox_min_xyz, dims_zyx, interpolation, True, min_value, outside_value)
+        rz, ry, rx = np.asarray(raw).shape
+        mx = (rx - 1, ry - 1, rz - 1)
+        wf = np.ones(dims_zyx, dtype=f32) if fusion_blending is None else \
+            blending_weight_affine(dims_zyx, bbox_min_xyz, ia, (0, 0, 0), mx, fusion_blending[j][0], fusion_blending[j][1])
+        wd = np.ones(dims_zyx, dtype=f32) if decon_blending is None else \
+            blending_weight_affine(dims_zyx, bbox_min_xyz, ia, (0, 0, 0), mx, decon_blending[j][0], decon_blending[j][1])
+        nz = wf != 0
+        sum_i = np.where(nz, sum_i + img.astype(f64) * wf.astype(f64), sum_i)
+        sum_w = np.where(nz, sum_w + wf.astype(f64), sum_w)
+        sum_d = sum_d + wd.astype(f64)
+    with np.errstate(all="ignore"):
+        fused = np.where(sum_w > 0, (sum_i / sum_w).astype(f32), f32(0)).astype(f32)
+    return fused, sum_d.astype(f32)
+
+
+# ---- PSF preparation: PSFPreparation.loadGroupTransformPSFs (M/process/deconvolution/util/PSFPreparation.java:41-89) ---------------
+def psf_normalize_minmax(psf: np.ndarray) -> np.ndarray:
+    """PSFExtraction.normalize (M/process/psf/PSFExtraction.java:453-473): (v - min) / (max - min) in double, stored as float."""
+    p = np.asarray(psf, dtype=np.float32).astype(np.float64)
+    return ((p - p.min()) / (p.max() - p.min())).astype(np.float32)
+
+
+def _apply_affine(m, x, y, z):
+    return [((x * m[4 * r] + y * m[4 * r + 1]) + z * m[4 * r + 2]) + m[4 * r + 3] for r in range(3)]
+
+
+def psf_transformed_geometry(dims_xyz, affine_row_packed):
+    """new size (odd per axis) and offset of PSFExtraction.transformPSF (:367-409): estimateBounds of the interval [0, dim-1]
+    (imglib2-realtransform: min / max over the 8 transformed corners), newSize = (int)size + 1 made odd, offset = A(center) - newSize/2
+    with center = dim / 2 (integer division)."""
+    m = np.asarray(affine_row_packed, dtype=np.float64).ravel()
+    pts = np.array([_apply_affine(m, float(cx), float(cy), float(cz))
+                    for cz in (0, dims_xyz[2] - 1) for cy in (0, dims_xyz[1] - 1) for cx in (0, dims_xyz[0] - 1)])
+    size = pts.max(axis=0) - pts.min(axis=0)
+    new = [int(size[d]) + 1 for d in range(3)]
+    new = [n + 1 if n % 2 == 0 else n for n in new]
+    ctr = _apply_affine(m, float(dims_xyz[0] // 2), float(dims_xyz[1] // 2), float(dims_xyz[2] // 2))
+    off = [ctr[d] - (new[d] // 2) for d in range(3)]
+    return new, off
+
+
+def psf_transform(psf: np.ndarray, affine_row_packed, inv_affine_row_packed) -> np.ndarray:
+    """PSFExtraction.getTransformedNormalizedPSF (:182-193) = normalize + transformPSF -> transform (:411-451): n-linear sampling of
+    the zero-extended PSF at inverse(model)(voxel + offset)."""
+    p = psf_normalize_minmax(psf)
+    dz, dy, dx = p.shape
+    new, off = psf_transformed_geometry((dx, dy, dz), affine_row_packed)
+    im = np.asarray(inv_affine_row_packed, dtype=np.float64).ravel()
+    z, y, x = np.meshgrid(np.arange(new[2], dtype=np.float64) + off[2], np.arange(new[1], dtype=np.float64) + off[1],
+                          np.arange(new[0], dtype=np.float64) + off[0], indexing="ij")
+    t = _apply_affine(im, x, y, z)
+    return nlinear3(p, t, extend_zero=True)
+
+
+def psf_average(psfs: Sequence[np.ndarray], use_max: bool = False) -> np.ndarray:
+    """PSFCombination.computeAverageImage (M/process/psf/PSFCombination.java:74-135): centre-aligned float accumulation into the
+    min (or max) size of all inputs (zero-extended target: samples outside are dropped), divided by the count in double."""
+    shapes = np.array([p.shape for p in psfs])
+    size = shapes.max(axis=0) if use_max else shapes.min(axis=0)
+    avg = np.zeros(tuple(size), dtype=np.float32)
+    ac = [s // 2 for s in size]
+    for p in psfs:
+        p = np.asarray(p, dtype=np.float32)
+        pc = [s // 2 for s in p.shape]
+        sl_a, sl_p = [], []
+        for d in range(3):
+            lo = ac[d] - pc[d]                       # position of psf sample 0 in the average
+            a0, a1 = max(0, lo), min(size[d], lo + p.shape[d])
+            sl_a.append(slice(a0, a1)); sl_p.append(slice(a0 - lo, a1 - lo))
+        avg[tuple(sl_a)] = (avg[tuple(sl_a)] + p[tuple(sl_p)]).astype(np.float32)
+    return (avg.astype(np.float64) / float(len(psfs))).astype(np.float32)
+
+
+def psf_make_same_size(psf: np.ndarray, size_zyx) -> np.ndarray:
+    """PSFCombination.makeSameSize (:182-212): centred copy into the new size, padded with the minimum of the input."""
+    p = np.asarray(psf, dtype=np.float32)
+    out = np.full(tuple(size_zyx), p.min(), dtype=np.float32)
+    idx = [np.arange(size_zyx[d]) - size_zyx[d] // 2 + p.shape[d] // 2 for d in range(3)]
+    ok = [(i >= 0) & (i < p.shape[d]) for d, i in enumerate(idx)]
+    zz, yy, xx = np.ix_(idx[0][ok[0]], idx[1][ok[1]], idx[2][ok[2]])
+    oz, oy, ox = np.ix_(np.nonzero(ok[0])[0], np.nonzero(ok[1])[0], np.nonzero(ok[2])[0])
+    out[oz, oy, ox] = p[zz, yy, xx]
+    return out
+
+
 def smooth_weights(w: np.ndarray, sumw: np.ndarray, max_diff_range=MAX_DIFF_RANGE, scaling_range=SCALING_RANGE) -> np.ndarray:
     """NormalizingRandomAccess.smoothWeights (NormalizingRandomAccess.java:183-201)."""
     f32 = np.float32

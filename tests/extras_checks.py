@@ -123,3 +123,72 @@ def check_affine_blending_weights(lib, oracle):
     a = oracle.blending_weight_affine(dims, (0, 0, 0), ident, (4, 3, 2), (40, 30, 25), (0, 0, 0), (12, 12, 12))
     b = oracle.blending_weight(dims, (4, 3, 2), (40, 30, 25), (0, 0, 0), (12, 12, 12))
     assert np.array_equal(a, b)
+
+
+# ---- the step before the loop: view materialisation and PSF preparation -----------------------------------------
+def _models():
+    """two rotated / anisotropically scaled views and their inverses (row-packed 3x4)"""
+    out = []
+    for th_deg, sz, tr in ((27.0, 1.7, (9.3, -2.25, 14.1)), (-14.0, 2.1, (4.2, 1.5, -3.75))):
+        th = np.deg2rad(th_deg)
+        fwd = np.array([[np.cos(th), 0.0, np.sin(th) * sz, tr[0]], [0.0, 1.0, 0.0, tr[1]], [-np.sin(th), 0.0, np.cos(th) * sz, tr[2]], [0, 0, 0, 1.0]])
+        out.append((fwd[:3].ravel(), np.linalg.inv(fwd)[:3].ravel()))
+    return out
+
+
+def check_fuse_group(lib, oracle, interpolation, with_blending):
+    """ProcessInputImages.fuseGroups on the device == oracle restatement, bit for bit: two rotated raw views fused into one virtual view
+    (image and summed weight), then used as the input of a view update"""
+    import mvrecon_b200 as m
+    rng = np.random.default_rng(11)
+    dims, bbox_min = (30, 36, 44), (-3, 1, 2)
+    raws = [(rng.random(s) * 300).astype(np.float32) for s in ((20, 36, 40), (18, 30, 38))]
+    raws[0][5:9, 10:20, 10:30] = 0.25                                   # below minValueImg: clamped to 1 inside the image
+    models = _models()
+    fb = [((2.0, 1.0, 0.5), (12.0, 10.0, 6.0)), ((1.0, 1.0, 1.0), (8.0, 8.0, 4.0))] if with_blending else None
+    db = [((-3.0, -3.0, -1.0), (12.0, 10.0, 6.0)), ((0.0, 0.0, 0.0), (6.0, 6.0, 3.0))] if with_blending else None
+    ref_img, ref_w = oracle.fuse_group(raws, [mi for _, mi in models], bbox_min, dims, interpolation, fb, db)
+    assert 0 < np.count_nonzero(ref_img) < ref_img.size
+    rv = [m.RawView(raws[j], models[j][1], interpolation, None if fb is None else fb[j], None if db is None else db[j]) for j in range(2)]
+    psf = oracle.synth_psf(0, 1, (5, 5, 5), (1.0, 1.0, 1.2))
+    dv = m.DeconViews([m.DeconView(m.FusedGroup(rv, bbox_min, dims), None, psf)], library=lib)
+    try:
+        got_img, got_w = dv.getImage(0), dv.getWeight(0)
+        assert np.array_equal(got_w, ref_w)
+        assert np.array_equal(got_img, ref_img)
+        # the materialised view drives the loop like an uploaded one
+        dv.normalizeWeights(1.0, False)
+        w = oracle.normalize_weights([ref_w])[0]
+        psi0 = np.full(dims, 50.0, np.float32)
+        dec = m.MultiViewDeconvolutionSeq(dv, 1, m.PsiInitFromRAI(psi0, [float(ref_img.max())]))
+        dec.runIterations()
+        k1, k2 = oracle.derive_kernels([psf], oracle.INDEPENDENT)
+        view = oracle.OracleView(ref_img, w, k1[0], k2[0], float(ref_img.max()))
+        want, _, _ = oracle.view_update_whole(psi0, view, 0.0, dtype=np.float64)
+        assert oracle.rel_l2(dec.getPSI(), want) < 2e-6
+    finally:
+        dv.close()
+
+
+def check_psf_preparation(lib, oracle):
+    """PSFPreparation.loadGroupTransformPSFs pieces vs the oracle restatement (host code: bit exact)"""
+    rng = np.random.default_rng(12)
+    psfs = [rng.random(s).astype(np.float32) for s in ((9, 11, 13), (11, 11, 11))]
+    models = _models()
+    t = [lib.psf_transform(p, a, ia) for p, (a, ia) in zip(psfs, models)]
+    for got, p, (a, ia) in zip(t, psfs, models):
+        want = oracle.psf_transform(p, a, ia)
+        assert got.shape == want.shape and all(s % 2 == 1 for s in got.shape)
+        assert np.array_equal(got, want)
+    for use_max in (False, True):
+        assert np.array_equal(lib.psf_average(t, use_max), oracle.psf_average(t, use_max))
+    avg = lib.psf_average(t)
+    assert np.array_equal(lib.psf_make_same_size(avg, (41, 15, 33)), oracle.psf_make_same_size(avg, (41, 15, 33)))
+    assert np.array_equal(lib.psf_make_same_size(avg, (5, 7, 3)), oracle.psf_make_same_size(avg, (5, 7, 3)))
+    import mvrecon_b200 as m
+    groups = [[(psfs[0], *models[0]), (psfs[1], *models[1])], [(psfs[1], *models[0])]]
+    got = m.loadGroupTransformPSFs(groups, True, lib)
+    a = oracle.psf_average([oracle.psf_transform(p, f, i) for p, f, i in groups[0]])
+    b = oracle.psf_average([oracle.psf_transform(p, f, i) for p, f, i in groups[1]])
+    size = tuple(max(a.shape[d], b.shape[d]) for d in range(3))
+    assert np.array_equal(got[0], oracle.psf_make_same_size(a, size)) and np.array_equal(got[1], oracle.psf_make_same_size(b, size))

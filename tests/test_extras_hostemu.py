@@ -24,3 +24,12 @@ def test_mul_iteration_matches_oracle(hostemu_lib, oracle, small_dataset, lam):
 
 def test_affine_blending_weights(hostemu_lib, oracle):
     X.check_affine_blending_weights(hostemu_lib, oracle)
+
+
+@pytest.mark.parametrize("interpolation,with_blending", [(1, True), (1, False), (0, True)])
+def test_fuse_group(hostemu_lib, oracle, interpolation, with_blending):
+    X.check_fuse_group(hostemu_lib, oracle, interpolation, with_blending)
+
+
+def test_psf_preparation(hostemu_lib, oracle):
+    X.check_psf_preparation(hostemu_lib, oracle)

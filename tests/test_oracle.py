@@ -188,3 +188,74 @@ def test_float32_oracle_noise_floor(oracle, small_dataset):
     a, _ = oracle.run_iterations_seq(psi0, views, 3, 0.0, dtype=np.float32)
     b, _ = oracle.run_iterations_seq(psi0, views, 3, 0.0, dtype=np.float64)
     assert oracle.rel_l2(a, b) < 1e-6
+
+
+# ---- view materialisation / PSF preparation: hand-derived known answers ---------------------------------------
+IDENT = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0]
+
+
+def test_transform_view_identity_and_strict_inside(oracle):
+    rng = np.random.default_rng(1)
+    raw = (rng.random((6, 7, 8)) * 10).astype(np.float32)
+    out = oracle.transform_view(raw, IDENT, (0, 0, 0), (6, 7, 8), interpolation=1)
+    # strictly inside (0, dim-1) only: the outermost voxel layer is "outside" = 0 (AbstractTransformedIntervalRandomAccess.java:80)
+    assert np.all(out[0] == 0) and np.all(out[-1] == 0) and np.all(out[:, 0] == 0) and np.all(out[:, :, -1] == 0)
+    np.testing.assert_array_equal(out[1:-1, 1:-1, 1:-1], np.maximum(np.float32(1), raw[1:-1, 1:-1, 1:-1]))
+    nn = oracle.transform_view(raw, IDENT, (0, 0, 0), (6, 7, 8), interpolation=0, has_min_value=False)
+    np.testing.assert_array_equal(nn[1:-1, 1:-1, 1:-1], raw[1:-1, 1:-1, 1:-1])
+
+
+def test_transform_view_translation_and_half_voxel(oracle):
+    rng = np.random.default_rng(2)
+    raw = (5 + rng.random((8, 8, 8)) * 10).astype(np.float32)
+    # world = raw + (2, 1, 0)  =>  inverse: raw = world - (2, 1, 0); bounding box starts at world (2, 1, 0)
+    inv = [1, 0, 0, -2, 0, 1, 0, -1, 0, 0, 1, 0]
+    out = oracle.transform_view(raw, inv, (2, 1, 0), (8, 8, 8))
+    np.testing.assert_array_equal(out[1:-1, 1:-1, 1:-1], raw[1:-1, 1:-1, 1:-1])
+    # half a voxel along x: mean of the two x neighbours, each product rounded to float first (FloatType.mul(double))
+    inv = [1, 0, 0, 0.5, 0, 1, 0, 0, 0, 0, 1, 0]
+    out = oracle.transform_view(raw, inv, (0, 0, 0), (8, 8, 8), has_min_value=False)
+    a, b = raw[3, 4, 2], raw[3, 4, 3]
+    want = np.float32(np.float32(np.float64(a) * 0.5) + np.float32(np.float64(b) * 0.5))
+    assert out[3, 4, 2] == want
+    assert out[3, 4, 7] == 0                                  # t_x = 7.5 is not < 7
+
+
+def test_fuse_group_average_and_weight_sum(oracle):
+    rng = np.random.default_rng(3)
+    a = (2 + rng.random((8, 8, 8))).astype(np.float32)
+    b = (4 + rng.random((8, 8, 8))).astype(np.float32)
+    img, w = oracle.fuse_group([a, b], [IDENT, IDENT], (0, 0, 0), (8, 8, 8))
+    inner = (slice(1, -1),) * 3
+    want = ((a.astype(np.float64) + b.astype(np.float64)) / 2.0).astype(np.float32)
+    np.testing.assert_array_equal(img[inner], want[inner])
+    assert np.all(w == 2)                                     # no blending given: constant 1 per view, summed
+    # one view with a blending weight of 0 near its border: there the other view alone defines the value
+    bl = [((1.0, 1.0, 1.0), (2.0, 2.0, 2.0)), ((-20.0, -20.0, -20.0), (2.0, 2.0, 2.0))]
+    img2, w2 = oracle.fuse_group([a, b], [IDENT, IDENT], (0, 0, 0), (8, 8, 8), fusion_blending=bl, decon_blending=bl)
+    assert img2[1, 4, 4] == b[1, 4, 4] and w2[1, 4, 4] == 1   # view a: distance 1 - border 1 = 0 -> weight 0
+    assert w2[4, 4, 4] == 2
+
+
+def test_psf_preparation_known_answers(oracle):
+    rng = np.random.default_rng(4)
+    psf = rng.random((5, 7, 9)).astype(np.float32)
+    n = oracle.psf_normalize_minmax(psf)
+    assert n.min() == 0 and n.max() == 1
+    new, off = oracle.psf_transformed_geometry((9, 7, 5), IDENT)
+    assert new == [9, 7, 5] and off == [0.0, 0.0, 0.0]
+    np.testing.assert_array_equal(oracle.psf_transform(psf, IDENT, IDENT), n)
+    # anisotropy correction: z scaled by 3 -> (5 - 1) * 3 + 1 = 13 planes, centre stays the centre
+    sc, isc = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 3, 0], [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 / 3, 0]
+    new, off = oracle.psf_transformed_geometry((9, 7, 5), sc)
+    assert new == [9, 7, 13] and off == [0.0, 0.0, 0.0]
+    t = oracle.psf_transform(psf, sc, isc)
+    assert t.shape == (13, 7, 9)
+    np.testing.assert_allclose(t[::3], n, rtol=0, atol=2e-7)
+    # average over the minimal size, centre aligned
+    big = np.zeros((7, 7, 7), np.float32); big[3, 3, 3] = 4
+    small = np.zeros((5, 5, 5), np.float32); small[2, 2, 2] = 2
+    avg = oracle.psf_average([big, small])
+    assert avg.shape == (5, 5, 5) and avg[2, 2, 2] == 3 and avg.sum() == 3
+    same = oracle.psf_make_same_size(small - 1, (7, 5, 9))
+    assert same.shape == (7, 5, 9) and same[3, 2, 4] == 1 and same.min() == -1 and same[0, 0, 0] == -1
