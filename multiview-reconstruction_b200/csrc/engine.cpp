@@ -810,7 +810,7 @@ void Engine::fuse_group_host(int v, const RawViewDev* views_host, int count, con
         MVD_CUDA_CHECK(cudaEventCreate(&e0)); MVD_CUDA_CHECK(cudaEventCreate(&e1));
         MVD_CUDA_CHECK(cudaEventRecord(e0, stream_));
 #endif
-        fuse_group(stream_, dv, count, vw.img_owned, vw.weight_owned, lut_dev_, cfg_.geom.vol, cfg_.geom.goff, bbox_min, min_value_img, outside_value);
+        fuse_group(stream_, dv, hv.data(), count, vw.img_owned, vw.weight_owned, lut_dev_, cfg_.geom.vol, cfg_.geom.goff, bbox_min, min_value_img, outside_value);
 #ifndef MVD_HOST_EMU
         MVD_CUDA_CHECK(cudaEventRecord(e1, stream_));
 #endif

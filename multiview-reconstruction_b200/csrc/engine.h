@@ -203,8 +203,8 @@ struct RawViewDev {
     int fusion_blend; float fusion_border[3], fusion_range[3];
     int decon_blend; float decon_border[3], decon_range[3];
 };
-void fuse_group(stream_t s, const RawViewDev* views_dev, int count, float* img_out, float* w_out, const double* lut_dev, const int vol[3],
-                const int goff[3], const int bbox_min[3], float min_value, float outside_value);
+void fuse_group(stream_t s, const RawViewDev* views_dev, const RawViewDev* views_host, int count, float* img_out, float* w_out,
+                const double* lut_dev, const int vol[3], const int goff[3], const int bbox_min[3], float min_value, float outside_value);
 // PSF preparation on the host (kernels are a few thousand voxels; psf_prep.cpp)
 void psf_transformed_geometry(const int dims[3], const double affine[12], int new_dims[3], double offset[3]);
 std::vector<float> psf_transform_normalized(const float* psf, const int dims[3], const double affine[12], const double inv_affine[12], int new_dims[3]);

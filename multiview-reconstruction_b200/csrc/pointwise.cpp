@@ -255,44 +255,58 @@ MVD_HD float nlinear3_at(const float* raw, const int dims[3], double t0, double 
 }
 
 struct FuseGroupKernel {
+    RawViewDev inl[4];                 // the first views travel as kernel parameters (constant bank), the rest is read from global memory
     const RawViewDev* views; int count;
     float* img_out; float* w_out; const double* lut;
     int nx, ny; int goff[3]; int bbox_min[3];
     float min_value, outside_value;
+    MVD_HD void one(const RawViewDev& v, double s0, double s1, double s2, double& sum_i, double& sum_w, double& sum_d) const {
+        double t[3];
+        for (int r = 0; r < 3; ++r)
+            t[r] = d_add(d_add(d_add(d_mul(s0, v.im[4 * r]), d_mul(s1, v.im[4 * r + 1])), d_mul(s2, v.im[4 * r + 2])), v.im[4 * r + 3]);
+        float val = outside_value;
+        if (t[0] > 0 && t[1] > 0 && t[2] > 0 && t[0] < (double)(v.dims[0] - 1) && t[1] < (double)(v.dims[1] - 1) && t[2] < (double)(v.dims[2] - 1)) {
+            float smp;
+            if (v.interpolation == 1) smp = nlinear3_at(v.raw, v.dims, t[0], t[1], t[2]);
+            else {                                  // Util.roundToLong: half away from zero (t > 0 here)
+                const long long rx = (long long)(t[0] + 0.5), ry = (long long)(t[1] + 0.5), rz = (long long)(t[2] + 0.5);
+                smp = v.raw[(rz * v.dims[1] + ry) * v.dims[0] + rx];
+            }
+            val = smp > min_value ? smp : min_value;                                   // Math.max(minValue, sample)
+        }
+        const float loc[3] = {(float)t[0], (float)t[1], (float)t[2]};                     // TransformedRasteredRandomAccess.java:96-114
+        const int dm1[3] = {v.dims[0] - 1, v.dims[1] - 1, v.dims[2] - 1};
+        const float wf = v.fusion_blend ? blend_weight_at(loc, dm1, v.fusion_border, v.fusion_range, lut) : 1.f;
+        const float wd = v.decon_blend ? blend_weight_at(loc, dm1, v.decon_border, v.decon_range, lut) : 1.f;
+        if (wf != 0.f) { sum_i = d_add(sum_i, d_mul((double)val, (double)wf)); sum_w = d_add(sum_w, (double)wf); }
+        sum_d = d_add(sum_d, (double)wd);
+    }
     MVD_HD void operator()(long long i) const {
-        const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((long long)nx * ny));
+        int x, y, z;
+        if (i < 0xFFFFFFFFLL) {                         // 32-bit index arithmetic whenever the box has fewer than 2^32 voxels
+            const unsigned u = (unsigned)i, r = u / (unsigned)nx;
+            x = (int)(u - r * (unsigned)nx); z = (int)(r / (unsigned)ny); y = (int)(r - (unsigned)z * (unsigned)ny);
+        } else {
+            x = (int)(i % nx); y = (int)((i / nx) % ny); z = (int)(i / ((long long)nx * ny));
+        }
         const double s0 = (double)((long long)x + goff[0] + bbox_min[0]), s1 = (double)((long long)y + goff[1] + bbox_min[1]),
                      s2 = (double)((long long)z + goff[2] + bbox_min[2]);
         double sum_i = 0, sum_w = 0, sum_d = 0;
-        for (int j = 0; j < count; ++j) {
-            const RawViewDev& v = views[j];
-            double t[3];
-            for (int r = 0; r < 3; ++r)
-                t[r] = d_add(d_add(d_add(d_mul(s0, v.im[4 * r]), d_mul(s1, v.im[4 * r + 1])), d_mul(s2, v.im[4 * r + 2])), v.im[4 * r + 3]);
-            float val = outside_value;
-            if (t[0] > 0 && t[1] > 0 && t[2] > 0 && t[0] < (double)(v.dims[0] - 1) && t[1] < (double)(v.dims[1] - 1) && t[2] < (double)(v.dims[2] - 1)) {
-                float smp;
-                if (v.interpolation == 1) smp = nlinear3_at(v.raw, v.dims, t[0], t[1], t[2]);
-                else {                                  // Util.roundToLong: half away from zero (t > 0 here)
-                    const long long rx = (long long)(t[0] + 0.5), ry = (long long)(t[1] + 0.5), rz = (long long)(t[2] + 0.5);
-                    smp = v.raw[(rz * v.dims[1] + ry) * v.dims[0] + rx];
-                }
-                val = smp > min_value ? smp : min_value;                                   // Math.max(minValue, sample)
-            }
-            const float loc[3] = {(float)t[0], (float)t[1], (float)t[2]};                     // TransformedRasteredRandomAccess.java:96-114
-            const int dm1[3] = {v.dims[0] - 1, v.dims[1] - 1, v.dims[2] - 1};
-            const float wf = v.fusion_blend ? blend_weight_at(loc, dm1, v.fusion_border, v.fusion_range, lut) : 1.f;
-            const float wd = v.decon_blend ? blend_weight_at(loc, dm1, v.decon_border, v.decon_range, lut) : 1.f;
-            if (wf != 0.f) { sum_i = d_add(sum_i, d_mul((double)val, (double)wf)); sum_w = d_add(sum_w, (double)wf); }
-            sum_d = d_add(sum_d, (double)wd);
-        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 4; ++j)
+            if (j < count) one(inl[j], s0, s1, s2, sum_i, sum_w, sum_d);
+        for (int j = 4; j < count; ++j) one(views[j], s0, s1, s2, sum_i, sum_w, sum_d);
         img_out[i] = sum_w > 0 ? (float)(sum_i / sum_w) : 0.f;
         w_out[i] = (float)sum_d;
     }
 };
-void fuse_group(stream_t s, const RawViewDev* views_dev, int count, float* img_out, float* w_out, const double* lut_dev, const int vol[3],
-                const int goff[3], const int bbox_min[3], float min_value, float outside_value) {
+void fuse_group(stream_t s, const RawViewDev* views_dev, const RawViewDev* views_host, int count, float* img_out, float* w_out,
+                const double* lut_dev, const int vol[3], const int goff[3], const int bbox_min[3], float min_value, float outside_value) {
     FuseGroupKernel k;
+    std::memset(&k, 0, sizeof(k));
+    for (int j = 0; j < count && j < 4; ++j) k.inl[j] = views_host[j];     // same records (device raw pointers) as views_dev
     k.views = views_dev; k.count = count; k.img_out = img_out; k.w_out = w_out; k.lut = lut_dev;
     k.nx = vol[0]; k.ny = vol[1];
     for (int d = 0; d < 3; ++d) { k.goff[d] = goff[d]; k.bbox_min[d] = bbox_min[d]; }
