@@ -313,6 +313,7 @@ void Convolver::conv(const float* src, float* dst, const cpx* khat, int ext, flo
 
 void Convolver::view_update(const float* psi_in, float* psi_out, const float* img, const float* weight, const cpx* k1hat,
                             const cpx* k2hat, float lambda, float min_value, float max_intensity, double* part_sum, float* part_max) {
+    if (xmode_ != 0) throw Error("internal: view updates need the real-packed x mode");
     int ti = 0;
     const int cp = chunk_planes_ > 0 ? chunk_planes_ : T_[2];
     for (const TileGeom& t : tiles_) {
@@ -359,6 +360,7 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
 }
 
 void Convolver::integral(const float* psi_in, const float* img, const cpx* k1hat, const cpx* k2hat, float* integral_out) {
+    if (xmode_ != 0) throw Error("internal: the quotient pass needs the real-packed x mode");
     for (const TileGeom& t : tiles_) {
         XArgs a = base_xargs(t);
         a.src = psi_in;
