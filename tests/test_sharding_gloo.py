@@ -180,3 +180,61 @@ def test_exchange_callback_and_two_exchange_scheme(hostemu_lib, oracle, tmp_path
     got = np.concatenate([np.load(tmp_path / f"part{r}.npy") for r in range(world)], axis=0 if axis == "z" else 1)
     assert got.shape == ref.shape
     assert oracle.rel_l2(got, ref) < 4e-6
+
+
+# ---- 2-d (y x z) grid of four boxes: corners must be right under both exchange schemes ----------------------------------------------
+DIMS_2D = (40, 44, 24)
+
+
+def _worker_grid(rank, world, port, lib_path, out_dir, scheme):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch.distributed as dist
+    import mvdecon_oracle as o
+    import mvrecon_b200 as m
+    from mvrecon_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = m.Lib(lib_path)
+    ds = o.make_synthetic(DIMS_2D, VIEWS, seed=8, **KW_CB)
+    views, psi0, avg = o.make_oracle_views(ds, o.EFFICIENT_BAYESIAN)
+    nz, ny, nx = DIMS_2D
+    py, pz = 2, 2
+    ry, rz = rank // pz, rank % pz
+    H = 2 if scheme == 1 else 4
+    ylo, yhi = sharding.slab_range(ny, py, ry)
+    zlo, zhi = sharding.slab_range(nz, pz, rz)
+    y0, y1 = sharding.extended_range(ylo, yhi, ny, H)
+    z0, z1 = sharding.extended_range(zlo, zhi, nz, H)
+    cut = lambda a: np.ascontiguousarray(a[z0:z1, y0:y1])
+    loc = [m.DeconView(cut(ds.images[v]), cut(ds.weights[v]), ds.psfs[v], m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(VIEWS)]
+    dv = m.DeconViews(loc, global_dims_zyx=DIMS_2D, library=lib, exchange_scheme=scheme,
+                      shard=(zlo, zhi, z0, z1 - z0), shard_y=(ylo, yhi, y0, y1 - y0))
+    dv.set_exchange_callback(sharding.host_exchange_callback(ry, rz, py, pz, lambda a, b: a * pz + b, dist))
+    dec = m.MultiViewDeconvolutionSeq(dv, 2, m.PsiInitFromRAI(cut(psi0), [v.max_intensity for v in views]))
+    dec.runIterations()
+    np.save(os.path.join(out_dir, f"box{rank}.npy"), dec.getPSI()[zlo - z0:zhi - z0, ylo - y0:yhi - y0])
+    dv.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("scheme", [0, 1])
+def test_four_boxes_2d_grid(hostemu_lib, oracle, tmp_path, scheme):
+    import torch.multiprocessing as mp
+    from mvrecon_b200 import sharding
+    world = 4
+    port = 33500 + (os.getpid() % 2000) + 13 * scheme
+    mp.start_processes(_worker_grid, args=(world, port, hostemu_lib.path, str(tmp_path), scheme), nprocs=world, join=True, start_method="spawn")
+    ds = oracle.make_synthetic(DIMS_2D, VIEWS, seed=8, **KW_CB)
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN)
+    ref, _ = oracle.run_iterations_seq(psi0, views, 2, 0.0, dtype=np.float64)
+    got = np.empty_like(ref, dtype=np.float32)
+    nz, ny, nx = DIMS_2D
+    for r in range(world):
+        ry, rz = r // 2, r % 2
+        ylo, yhi = sharding.slab_range(ny, 2, ry)
+        zlo, zhi = sharding.slab_range(nz, 2, rz)
+        got[zlo:zhi, ylo:yhi] = np.load(tmp_path / f"box{r}.npy")
+    assert oracle.rel_l2(got, ref) < 4e-6
