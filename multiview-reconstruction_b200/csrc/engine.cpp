@@ -202,6 +202,7 @@ Convolver::Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], in
 Convolver::~Convolver() {
     dev::free_(work_);
     dev::free_(kpad_);
+    dev::free_(kdev_);
 #ifndef MVD_HOST_EMU
     for (void* e : prof_events_) cudaEventDestroy((cudaEvent_t)e);
 #endif
@@ -268,16 +269,28 @@ void Convolver::col(int axis, int mode, const cpx* khat, int z0, int z1) {
 }
 
 cpx* Convolver::build_khat(const float* kernel_host, const int kd[3]) {
+    cpx* khat = (cpx*)dev::alloc(sizeof(cpx) * tile_elems());
+    try { build_khat_into(khat, kernel_host, kd); } catch (...) { dev::free_(khat); throw; }
+    return khat;
+}
+
+// No cudaFree and no synchronisation in here: cudaFree waits for the whole device, i.e. also for the view uploads that run on the copy
+// stream while the spectra are built (DeconViews with async upload).  The staging buffers live as long as the plan.
+void Convolver::build_khat_into(cpx* khat, const float* kernel_host, const int kd[3]) {
     for (int d = 0; d < 3; ++d)
         if (kd[d] > T_[d] || kd[d] < 1) throw Error("kernel larger than the FFT tile");
     const size_t nk = (size_t)kd[0] * kd[1] * kd[2];
     const size_t nt = (size_t)T_[0] * T_[1] * T_[2];
     if (!kpad_) kpad_ = (float*)dev::alloc(sizeof(float) * nt);
-    float* kdev = (float*)dev::alloc(sizeof(float) * nk);
-    dev::h2d(kdev, kernel_host, sizeof(float) * nk, stream_);
+    if (nk > kdev_cap_) {
+        float* bigger = (float*)dev::alloc(sizeof(float) * nk);
+        if (kdev_) { dev::sync(stream_); dev::free_(kdev_); }
+        kdev_ = bigger; kdev_cap_ = nk;
+    }
+    dev::h2d(kdev_, kernel_host, sizeof(float) * nk, stream_);          // pageable source: the call returns once the data is staged
     dev::zero(kpad_, sizeof(float) * nt, stream_);
     const double nfft = (double)M_ * (double)T_[1] * (double)T_[2];
-    PlaceKernel pk{kdev, kpad_, kd[0], kd[1], kd[2], T_[0], T_[1], T_[2], (float)(1.0 / nfft), xmode_ == 0 ? 1 : 0};
+    PlaceKernel pk{kdev_, kpad_, kd[0], kd[1], kd[2], T_[0], T_[1], T_[2], (float)(1.0 / nfft), xmode_ == 0 ? 1 : 0};
     pfor((long long)nk, pk, stream_);
     // forward transform of the padded kernel through the very same passes (scrambled order matches by construction)
     TileGeom t;
@@ -289,11 +302,7 @@ cpx* Convolver::build_khat(const float* kernel_host, const int kd[3]) {
     xpass(X_FWD, a);
     col(1, COL_FWD, nullptr);
     col(2, COL_FWD, nullptr);
-    cpx* khat = (cpx*)dev::alloc(sizeof(cpx) * tile_elems());
     dev::d2d(khat, work_, sizeof(cpx) * tile_elems(), stream_);
-    dev::sync(stream_);
-    dev::free_(kdev);
-    return khat;
 }
 
 void Convolver::conv(const float* src, float* dst, const cpx* khat, int ext, float ext_value) {
@@ -457,6 +466,7 @@ Engine::~Engine() {
     comm_.reset();
     for (float* p : integral_) dev::free_(p);
     dev::free_(lut_dev_); dev::free_(acc_dev_); dev::free_(max_dev_);
+    dev::free_(small_buf_); dev::free_(small_khat_);
     conv_.reset();
     tables_.reset();
     dev::stream_destroy(stream_);
@@ -533,16 +543,18 @@ std::vector<float> Engine::conv_same(const std::vector<float>& in, const int d[3
         small_conv_.reset(new Convolver(g, r1, r2, 0, cfg_.max_len, stream_, tables_.get()));
     }
     const size_t n = in.size();
-    float* s = (float*)dev::alloc(sizeof(float) * n * 2);
-    cpx* khat = nullptr;
-    try {
-        dev::h2d(s, in.data(), sizeof(float) * n, stream_);
-        khat = small_conv_->build_khat(k.data(), kd);
-        small_conv_->conv(s, s + n, khat, EXT_ZERO, 0.f);
-        dev::d2h(out.data(), s + n, sizeof(float) * n, stream_);
+    if (2 * n > small_buf_cap_ || small_conv_->tile_elems() > small_khat_cap_) {       // persistent scratch: no cudaFree per call (see build_khat_into)
         dev::sync(stream_);
-    } catch (...) { dev::free_(s); dev::free_(khat); throw; }
-    dev::free_(s); dev::free_(khat);
+        dev::free_(small_buf_); dev::free_(small_khat_);
+        small_buf_ = (float*)dev::alloc(sizeof(float) * n * 2); small_buf_cap_ = 2 * n;
+        small_khat_ = (cpx*)dev::alloc(sizeof(cpx) * small_conv_->tile_elems()); small_khat_cap_ = small_conv_->tile_elems();
+    }
+    float* s = small_buf_;
+    dev::h2d(s, in.data(), sizeof(float) * n, stream_);
+    small_conv_->build_khat_into(small_khat_, k.data(), kd);
+    small_conv_->conv(s, s + n, small_khat_, EXT_ZERO, 0.f);
+    dev::d2h(out.data(), s + n, sizeof(float) * n, stream_);
+    dev::sync(stream_);
     return out;
 }
 

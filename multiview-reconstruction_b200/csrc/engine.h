@@ -79,6 +79,7 @@ class Convolver {
 
     // kernel (x fastest, dims kd) -> resident spectrum (scale 1/Nfft folded in); caller owns the buffer
     cpx* build_khat(const float* kernel_host, const int kd[3]);
+    void build_khat_into(cpx* khat, const float* kernel_host, const int kd[3]);    // asynchronous on the stream; khat holds tile_elems()
     // dst(own box) = src (*) kernel, src extended by ext
     void conv(const float* src, float* dst, const cpx* khat, int ext, float ext_value);
     // one fused view update (P1..P9) over all tiles; partial stats -> part_sum/part_max [num_tiles*parts_per_tile]
@@ -106,6 +107,8 @@ class Convolver {
     Tables* tables_;
     cpx* work_ = nullptr;
     float* kpad_ = nullptr;
+    float* kdev_ = nullptr;     // kernel staging, grows on demand
+    size_t kdev_cap_ = 0;
     std::function<void(cpx*, const TileGeom&)> mid_exchange_;
     // software L2 prefetch distance in CTAs for the x, y and z passes (MVD_PF_X / MVD_PF_Y / MVD_PF_Z override)
     int pf_x_ = 74, pf_y_ = 296, pf_z_ = 148;
@@ -304,6 +307,8 @@ class Engine {
     stream_t copy_stream_ = nullptr;
     std::unique_ptr<Convolver> small_conv_;   // cached plan of the PSF-derivation convolutions
     int small_dims_[3] = {0, 0, 0}, small_kd_[3] = {0, 0, 0};
+    float* small_buf_ = nullptr; size_t small_buf_cap_ = 0;      // scratch of conv_same, reused across the derivation
+    cpx* small_khat_ = nullptr; size_t small_khat_cap_ = 0;
     void derive_kernels();
     std::vector<float> conv_same(const std::vector<float>& in, const int d[3], const std::vector<float>& k, const int kd[3]);
 
