@@ -199,6 +199,12 @@ MVD_API int mvd_synchronize(mvd_context* ctx);
 MVD_API int mvd_fetch_stats(mvd_context* ctx, int count, double* stats);
 
 /* Introspection for benchmarks / multi-GPU hosts */
+/* The tile planner on its own (csrc/engine.cpp plan_axis): how an axis of the fused volume of size gdim, of which this context owns
+ * [own_lo, own_hi), is cut into FFT tiles when the two chained kernels reach (r1_lo, r1_hi) and (r2_lo, r2_hi) samples below / above a
+ * voxel.  is_x: the x axis (real-packed, tile lengths 2 * FFT length); two_exchanges: exchange scheme 1 on a sharded axis.  Returns the tile
+ * length and up to cap tiles as triples {origin, valid_lo, valid_hi} (global coordinates).  Hosts use it to size shards (sharding.py).   */
+MVD_API int mvd_plan_axis(int gdim, int own_lo, int own_hi, int r1_lo, int r1_hi, int r2_lo, int r2_hi, int is_x, int max_fft_len,
+                          int two_exchanges, int* tile_len, int* tiles, int cap, int* num_tiles);
 MVD_API int mvd_tile_info(mvd_context* ctx, int tile_dims[3], int* num_tiles, double* fft_volume_ratio, int* launches_per_view_update);
 MVD_API int mvd_halo_planes(mvd_context* ctx, int* lo, int* hi);            /* z planes needed beyond the owned slab       */
 MVD_API int mvd_halo_rows(mvd_context* ctx, int* lo, int* hi);              /* y rows needed beyond the owned box (y sharding) */

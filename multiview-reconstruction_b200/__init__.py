@@ -126,6 +126,7 @@ SYMBOLS = {
     "mvd_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mvd_set_exchange_callback": (C.c_int, [C.c_void_p, EXCHANGE_FN, C.c_void_p]),
     "mvd_exchange_transport": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "mvd_plan_axis": (C.c_int, [C.c_int] * 10 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
     "mvd_fuse_group": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_RawView), C.c_int, C.POINTER(C.c_int), C.c_float, C.c_float]),
     "mvd_last_fuse_group_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "mvd_psf_transformed_dims": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -228,6 +229,16 @@ class Lib:
         out = np.empty(tuple(int(x) for x in size_zyx), dtype=np.float32)
         self.check(self.dll.mvd_psf_make_same_size(_fp(psf), _i3(_xyz(psf)), _i3(_xyz(out)), _fp(out)))
         return out
+
+    def plan_axis(self, gdim: int, own_lo: int, own_hi: int, r1=(0, 0), r2=(0, 0), is_x: bool = False, max_fft_len: int = 0,
+                  two_exchanges: bool = False):
+        """the library's tile planner for one axis: (tile length, [(origin, valid_lo, valid_hi), ...])"""
+        T, n = C.c_int(), C.c_int()
+        cap = 4096
+        buf = (C.c_int * (3 * cap))()
+        self.check(self.dll.mvd_plan_axis(int(gdim), int(own_lo), int(own_hi), int(r1[0]), int(r1[1]), int(r2[0]), int(r2[1]), int(is_x),
+                                          int(max_fft_len), int(two_exchanges), C.byref(T), buf, cap, C.byref(n)))
+        return T.value, [(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]) for i in range(min(n.value, cap))]
 
     def getNumDevicesCUDA(self) -> int:
         return int(self.dll.getNumDevicesCUDA())

@@ -312,6 +312,21 @@ int mvd_psf_make_same_size(const float* psf, const int dims[3], const int new_di
         std::copy(r.begin(), r.end(), out);
     });
 }
+int mvd_plan_axis(int gdim, int own_lo, int own_hi, int r1_lo, int r1_hi, int r2_lo, int r2_hi, int is_x, int max_fft_len, int two_exchanges,
+                  int* tile_len, int* tiles, int cap, int* num_tiles) {
+    return guarded([&] {
+        require(tile_len && num_tiles, "null argument");
+        require(gdim > 0 && own_lo >= 0 && own_hi <= gdim && own_lo < own_hi, "bad axis range");
+        require(r1_lo >= 0 && r1_hi >= 0 && r2_lo >= 0 && r2_hi >= 0, "negative reach");
+        const AxisTiling t = plan_axis(gdim, own_lo, own_hi, Reach{r1_lo, r1_hi}, Reach{r2_lo, r2_hi}, is_x != 0, max_fft_len > 0 ? max_fft_len : 1152,
+                                       two_exchanges != 0);
+        *tile_len = t.T;
+        *num_tiles = (int)t.tiles.size();
+        for (int i = 0; tiles && i < cap && i < (int)t.tiles.size(); ++i) {
+            tiles[3 * i] = t.tiles[(size_t)i].org; tiles[3 * i + 1] = t.tiles[(size_t)i].lo; tiles[3 * i + 2] = t.tiles[(size_t)i].hi;
+        }
+    });
+}
 int mvd_exchange_transport(mvd_context* ctx, int* transport) {
     return guarded([&] { require(ctx && transport, "null argument"); *transport = ctx->engine->exchange_transport(); });
 }

