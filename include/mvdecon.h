@@ -134,6 +134,15 @@ MVD_API int mvd_set_max_intensities(mvd_context* ctx, const float* max_per_view)
  * exchanged afterwards; the maxima are per shard and must be all-reduced by the host).                                               */
 enum { MVD_PSI_FUSED_BLURRED = 0, MVD_PSI_AVG = 1, MVD_PSI_APPROX_AVG = 2 };
 MVD_API int mvd_psi_init(mvd_context* ctx, int type, double sigma, double* avg_out, float* max_out);
+/* PsiInitFromFile (M/process/deconvolution/init/PsiInitFromFile.java:44-93): psi := the TIFF stack at `path` opened as 32 bit (dimensions
+ * must equal the volume, else the call fails like the reference returns false), then avg / max[] from PsiInitAvgPrecise (precise != 0) or
+ * PsiInitAvgApprox with setImgToAvg(false).  mvd_tiff_dims / mvd_tiff_read / mvd_tiff_write: the TIFF subset behind it and behind the
+ * result export (Save3dTIFF): uncompressed single-channel stacks, 8/16/32-bit integer or 32-bit float in, 32-bit float out with an ImageJ
+ * description; dims (x,y,z).  Unsharded contexts only.                                                                              */
+MVD_API int mvd_psi_init_from_file(mvd_context* ctx, const char* path, int precise, double* avg_out, float* max_out);
+MVD_API int mvd_tiff_dims(const char* path, int dims[3]);
+MVD_API int mvd_tiff_read(const char* path, float* out);
+MVD_API int mvd_tiff_write(const char* path, const float* data, const int dims[3]);
 
 /* Weight masks on the device.  mvd_make_blending_weights: cosine blending of view v's axis-aligned box [box_min, box_max] (global
  * integer coordinates, inclusive; BlendingRealRandomAccess.computeWeight, M/process/fusion/transformed/weights/BlendingRealRandomAccess.java:95-130)

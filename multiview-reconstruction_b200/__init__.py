@@ -126,6 +126,10 @@ SYMBOLS = {
     "mvd_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mvd_set_exchange_callback": (C.c_int, [C.c_void_p, EXCHANGE_FN, C.c_void_p]),
     "mvd_exchange_transport": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "mvd_psi_init_from_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, _D, _F]),
+    "mvd_tiff_dims": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
+    "mvd_tiff_read": (C.c_int, [C.c_char_p, _F]),
+    "mvd_tiff_write": (C.c_int, [C.c_char_p, _F, C.POINTER(C.c_int)]),
     "mvd_plan_axis": (C.c_int, [C.c_int] * 10 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
     "mvd_fuse_group": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_RawView), C.c_int, C.POINTER(C.c_int), C.c_float, C.c_float]),
     "mvd_last_fuse_group_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
@@ -229,6 +233,18 @@ class Lib:
         out = np.empty(tuple(int(x) for x in size_zyx), dtype=np.float32)
         self.check(self.dll.mvd_psf_make_same_size(_fp(psf), _i3(_xyz(psf)), _i3(_xyz(out)), _fp(out)))
         return out
+
+    def tiff_read(self, path: str) -> np.ndarray:
+        """a TIFF stack opened as 32 bit, [z, y, x]"""
+        d = (C.c_int * 3)()
+        self.check(self.dll.mvd_tiff_dims(os.fsencode(path), d))
+        out = np.empty((d[2], d[1], d[0]), dtype=np.float32)
+        self.check(self.dll.mvd_tiff_read(os.fsencode(path), _fp(out)))
+        return out
+
+    def tiff_write(self, path: str, vol: np.ndarray) -> None:
+        vol = _f32(vol)
+        self.check(self.dll.mvd_tiff_write(os.fsencode(path), _fp(vol), _i3(_xyz(vol))))
 
     def plan_axis(self, gdim: int, own_lo: int, own_hi: int, r1=(0, 0), r2=(0, 0), is_x: bool = False, max_fft_len: int = 0,
                   two_exchanges: bool = False):
@@ -673,6 +689,27 @@ class PsiInitAvgApprox(_PsiInitDevice):
     TYPE = 2
 
 
+class PsiInitFromFile(_PsiInitDevice):
+    """M/process/deconvolution/init/PsiInitFromFile.java:44-93: psi from a TIFF stack opened as 32 bit, avg / max[] from PsiInitAvgPrecise
+    (precise) or PsiInitAvgApprox with setImgToAvg(false).  runInitialization returns False (like the reference) when the file cannot be
+    loaded or its dimensions differ from the volume."""
+
+    def __init__(self, psiStartFile: str, precise: bool):
+        super().__init__(0.0)
+        self.psiStartFile, self.precise = str(psiStartFile), bool(precise)
+
+    def runInitialization(self, views: "DeconViews") -> bool:
+        avg = C.c_double()
+        mx = (C.c_float * len(views.getViews()))()
+        rc = views.lib.dll.mvd_psi_init_from_file(views._ctx, os.fsencode(self.psiStartFile), int(self.precise), C.byref(avg), mx)
+        if rc != 0:
+            self.error = views.lib.dll.mvd_last_error().decode()
+            return False
+        self.avg = float(avg.value)
+        self.max = np.array(list(mx), dtype=np.float32)
+        return True
+
+
 class MultiViewDeconvolutionSeq:
     """MultiViewDeconvolution + MultiViewDeconvolutionSeq (M/process/deconvolution/MultiViewDeconvolution.java:90-200,
     MultiViewDeconvolutionSeq.java:58-180): OSEM loop, psi updated after every view, resident on the device."""
@@ -683,8 +720,8 @@ class MultiViewDeconvolutionSeq:
         self.it = 0
         self.lib = views.lib
         if isinstance(psiInit, _PsiInitDevice):              # psiInit.runInitialization( psi, views, service ), MultiViewDeconvolution.java:115-135
-            psiInit.runInitialization(views)
-            self.max = np.asarray(psiInit.getMax(), dtype=np.float32)
+            ok = psiInit.runInitialization(views)
+            self.max = np.asarray(psiInit.getMax(), dtype=np.float32) if ok else None        # initWasSuccessful() == False
         else:
             self.max = np.asarray(psiInit.getMax(), dtype=np.float32)
             if self.max.shape != (len(views.getViews()),):

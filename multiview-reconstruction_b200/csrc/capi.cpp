@@ -312,6 +312,35 @@ int mvd_psf_make_same_size(const float* psf, const int dims[3], const int new_di
         std::copy(r.begin(), r.end(), out);
     });
 }
+int mvd_psi_init_from_file(mvd_context* ctx, const char* path, int precise, double* avg_out, float* max_out) {
+    return guarded([&] {
+        require(ctx && path, "null argument");
+        Engine& e = *ctx->engine;
+        const Geometry& g = e.config().geom;
+        int d[3];
+        const std::vector<float> img = tiff_read_f32(path, d);
+        for (int a = 0; a < 3; ++a) {
+            require(g.vol[a] == g.gdim[a], "PsiInitFromFile needs an unsharded context");
+            if (d[a] != g.gdim[a]) throw Error("Image dimensions do not match: the start image differs from the deconvolved volume");
+        }
+        e.set_psi_host(img.data());
+        e.psi_init(precise ? PSI_AVG : PSI_APPROX_AVG, 0.0, avg_out, max_out, false);
+    });
+}
+int mvd_tiff_dims(const char* path, int dims[3]) {
+    return guarded([&] { require(path && dims, "null argument"); tiff_dims(path, dims); });
+}
+int mvd_tiff_read(const char* path, float* out) {
+    return guarded([&] {
+        require(path && out, "null argument");
+        int d[3];
+        const std::vector<float> img = tiff_read_f32(path, d);
+        std::copy(img.begin(), img.end(), out);
+    });
+}
+int mvd_tiff_write(const char* path, const float* data, const int dims[3]) {
+    return guarded([&] { require(path && data && dims, "null argument"); tiff_write_f32(path, data, dims); });
+}
 int mvd_plan_axis(int gdim, int own_lo, int own_hi, int r1_lo, int r1_hi, int r2_lo, int r2_hi, int is_x, int max_fft_len, int two_exchanges,
                   int* tile_len, int* tiles, int cap, int* num_tiles) {
     return guarded([&] {

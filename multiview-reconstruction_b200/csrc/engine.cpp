@@ -690,7 +690,7 @@ void Engine::ensure_stats_slot() {
 // PsiInit on the device (M/process/deconvolution/init/PsiInitBlurredFused.java:63-127, PsiInitAvgPrecise.java:52-112,
 // PsiInitAvgApprox.java:47-99)
 // ------------------------------------------------------------------------------------------------
-void Engine::psi_init(int type, double sigma, double* avg_out, float* max_out) {
+void Engine::psi_init(int type, double sigma, double* avg_out, float* max_out, bool set_img_to_avg) {
     dev::set_device(cfg_.device);
     const int V = cfg_.num_views;
     if (V > MVD_MAX_VIEWS) throw Error("too many views for the device PsiInit");
@@ -724,7 +724,7 @@ void Engine::psi_init(int type, double sigma, double* avg_out, float* max_out) {
         avg_reported = avg;
         if (type == PSI_AVG) {
             if (sharded) throw Error("PsiInit AVG on a sharded context needs the global average: initialise psi from the host");
-            fill_volume(stream_, psi_[cur_], n, (float)avg);
+            if (set_img_to_avg) fill_volume(stream_, psi_[cur_], n, (float)avg);
         } else {
             // Gauss3.gauss(sigma, extendMirrorSingle(psi), psi) -- separable Gaussian expressed as one 3-d kernel through the FFT passes
             const std::vector<double> half = gauss3_halfkernel(sigma);
@@ -763,7 +763,7 @@ void Engine::psi_init(int type, double sigma, double* avg_out, float* max_out) {
         avg /= (double)V;
         if (avg != avg) avg = 1.0;
         avg_reported = -1.0;                                 // PsiInitAvgApprox.getAvg(): the field is shadowed by a local (:40,57,80)
-        fill_volume(stream_, psi_[cur_], n, (float)avg);
+        if (set_img_to_avg) fill_volume(stream_, psi_[cur_], n, (float)avg);
     } else {
         throw Error("unknown PsiInit type");
     }

@@ -213,6 +213,10 @@ void psf_transformed_geometry(const int dims[3], const double affine[12], int ne
 std::vector<float> psf_transform_normalized(const float* psf, const int dims[3], const double affine[12], const double inv_affine[12], int new_dims[3]);
 std::vector<float> psf_average(const float* const* psfs, const int (*dims)[3], int count, bool use_max, int out_dims[3]);
 std::vector<float> psf_make_same_size(const float* psf, const int dims[3], const int new_dims[3]);
+// TIFF stacks at the boundary (tiff_io.cpp): PsiInitFromFile / Save3dTIFF
+void tiff_dims(const char* path, int dims[3]);
+std::vector<float> tiff_read_f32(const char* path, int dims[3]);
+void tiff_write_f32(const char* path, const float* data, const int dims[3]);
 void normalize_weights(stream_t s, const WeightPtrs& w, int V, long long n, double osem, bool smooth, float max_diff_range, float scaling_range);
 void mul_combine(stream_t st, const MulPtrs& p, int V, const float* psi_in, float* psi_out, long long n, long long own0, long long own1, float lambda,
                  float min_value, float max_intensity, double* stats_dev, float* scratch_max_dev);
@@ -258,7 +262,8 @@ class Engine {
     float max_intensity(int v) const { return views_[v].max_intensity; }
 
     // PsiInit on the device (PsiInitBlurredFused / PsiInitAvgPrecise / PsiInitAvgApprox): sets psi and the per-view maxima
-    void psi_init(int type, double sigma, double* avg_out, float* max_out);
+    // set_img_to_avg = false: only the statistics (PsiInitAvg*.setImgToAvg(false), used by PsiInitFromFile), psi stays as it is
+    void psi_init(int type, double sigma, double* avg_out, float* max_out, bool set_img_to_avg = true);
     // weight masks on the device: cosine blending of a view's box, then NormalizingRandomAccess over all views
     void make_blending_weights(int v, const int box_min[3], const int box_max[3], const float border[3], const float blending[3],
                                const double* inv_affine = nullptr, const int* bbox_offset = nullptr);

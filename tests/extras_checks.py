@@ -192,3 +192,66 @@ def check_psf_preparation(lib, oracle):
     b = oracle.psf_average([oracle.psf_transform(p, f, i) for p, f, i in groups[1]])
     size = tuple(max(a.shape[d], b.shape[d]) for d in range(3))
     assert np.array_equal(got[0], oracle.psf_make_same_size(a, size)) and np.array_equal(got[1], oracle.psf_make_same_size(b, size))
+
+
+# ---- TIFF stacks at the boundary: PsiInitFromFile / result export ----------------------------------------------------------------------
+def check_tiff_io_and_psi_init_from_file(lib, oracle, small_dataset, tmp_path):
+    import mvrecon_b200 as m
+    from PIL import Image
+    ds = small_dataset
+    rng = np.random.default_rng(21)
+    vol = (rng.random(ds.dims_zyx) * 500).astype(np.float32)
+    # writer -> independent reader (PIL)
+    p1 = str(tmp_path / "ours.tif")
+    lib.tiff_write(p1, vol)
+    with Image.open(p1) as im:
+        assert im.n_frames == vol.shape[0] and im.mode == "F"
+        for z in (0, vol.shape[0] // 2, vol.shape[0] - 1):
+            im.seek(z)
+            assert np.array_equal(np.asarray(im, dtype=np.float32), vol[z])
+    assert np.array_equal(lib.tiff_read(p1), vol)
+    # independent writer (PIL) -> reader: float, 16-bit and 8-bit stacks are opened "as 32 bit"
+    for dtype, mode in ((np.float32, "F"), (np.uint16, "I;16"), (np.uint8, "L")):
+        src = vol.astype(dtype)
+        frames = [Image.fromarray(src[z]) for z in range(src.shape[0])]
+        assert frames[0].mode == mode
+        p2 = str(tmp_path / f"pil_{mode.replace(';', '')}.tif")
+        frames[0].save(p2, save_all=True, append_images=frames[1:], compression=None)
+        got = lib.tiff_read(p2)
+        assert got.dtype == np.float32 and np.array_equal(got, src.astype(np.float32))
+    # big-endian, hand-built single-slice file
+    be = bytearray(b"MM\x00\x2a\x00\x00\x00\x08")
+    w, h = 3, 2
+    entries = [(256, 3, 1, w << 16), (257, 3, 1, h << 16), (258, 3, 1, 16 << 16), (259, 3, 1, 1 << 16), (273, 4, 1, 8 + 2 + 12 * 7 + 4),
+               (277, 3, 1, 1 << 16), (279, 4, 1, w * h * 2)]
+    be += len(entries).to_bytes(2, "big")
+    for tag, typ, cnt, val in entries:
+        be += tag.to_bytes(2, "big") + typ.to_bytes(2, "big") + cnt.to_bytes(4, "big") + val.to_bytes(4, "big")
+    be += (0).to_bytes(4, "big") + b"".join(int(v).to_bytes(2, "big") for v in (1, 2, 3, 40000, 5, 6))
+    p3 = str(tmp_path / "be.tif")
+    open(p3, "wb").write(bytes(be))
+    assert np.array_equal(lib.tiff_read(p3), np.array([[[1, 2, 3], [40000, 5, 6]]], np.float32))
+    # errors are messages, not crashes
+    open(tmp_path / "junk.tif", "wb").write(b"not a tiff at all")
+    with pytest.raises(m.MvdError, match="TIFF"):
+        lib.tiff_read(str(tmp_path / "junk.tif"))
+    # PsiInitFromFile: psi = file, statistics from the views without touching psi
+    dv = m.DeconViews([m.DeconView(ds.images[v], ds.weights[v], ds.psfs[v]) for v in range(3)], library=lib)
+    try:
+        for precise in (True, False):
+            init = m.PsiInitFromFile(p1, precise)
+            dec = m.MultiViewDeconvolutionSeq(dv, 0, init)
+            assert dec.initWasSuccessful()
+            assert np.array_equal(dec.getPSI(), vol)
+            if precise:
+                _, ref_max, ref_avg = oracle.psi_init_avg_precise(ds.images, set_img_to_avg=False, psi=vol.copy())
+                assert abs(init.getAvg() - ref_avg) < 1e-9 * ref_avg
+            else:
+                _, ref_max, _ = oracle.psi_init_avg_approx(ds.images, set_img_to_avg=False, psi=vol.copy())
+                assert init.getAvg() == -1
+            assert np.array_equal(init.getMax(), ref_max)
+        bad = m.PsiInitFromFile(p3, True)                       # wrong dimensions: the reference returns false
+        assert not m.MultiViewDeconvolutionSeq(dv, 0, bad).initWasSuccessful() and "dimensions" in bad.error
+        assert not m.MultiViewDeconvolutionSeq(dv, 0, m.PsiInitFromFile(str(tmp_path / "missing.tif"), True)).initWasSuccessful()
+    finally:
+        dv.close()

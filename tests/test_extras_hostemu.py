@@ -33,3 +33,7 @@ def test_fuse_group(hostemu_lib, oracle, interpolation, with_blending):
 
 def test_psf_preparation(hostemu_lib, oracle):
     X.check_psf_preparation(hostemu_lib, oracle)
+
+
+def test_tiff_io_and_psi_init_from_file(hostemu_lib, oracle, small_dataset, tmp_path):
+    X.check_tiff_io_and_psi_init_from_file(hostemu_lib, oracle, small_dataset, tmp_path)
