@@ -66,3 +66,56 @@ def test_hostemu_reproduces_golden(hostemu_lib, oracle, gold):
         assert oracle.rel_l2(dec.getPSI(), gold["psi_it4"]) <= REL_TOL(4)
     finally:
         dv.close()
+
+
+# ---- the step before the loop (tests/golden/prep_case.npz, made by tests/golden/make_golden_prep.py) --------------------------------
+@pytest.fixture(scope="module")
+def prep():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prep_case.npz"))
+
+
+def _prep_inputs(g):
+    dims, bb = tuple(int(x) for x in g["dims_zyx"]), tuple(int(x) for x in g["bbox_min_xyz"])
+    fb = [(tuple(g["fusion_blending"][j][0]), tuple(g["fusion_blending"][j][1])) for j in range(2)]
+    db = [(tuple(g["decon_blending"][j][0]), tuple(g["decon_blending"][j][1])) for j in range(2)]
+    return dims, bb, fb, db
+
+
+def test_oracle_reproduces_prep_golden(oracle, prep):
+    g = prep
+    dims, bb, fb, db = _prep_inputs(g)
+    for j in range(2):
+        assert np.array_equal(oracle.transform_view(g[f"raw{j}"], g[f"inv_affine{j}"], bb, dims, 1), g[f"view_linear{j}"])
+        assert np.array_equal(oracle.transform_view(g[f"raw{j}"], g[f"inv_affine{j}"], bb, dims, 0), g[f"view_nearest{j}"])
+        assert np.array_equal(oracle.psf_transform(g[f"psf{j}"], g[f"affine{j}"], g[f"inv_affine{j}"]), g[f"psf_t{j}"])
+    img, w = oracle.fuse_group([g["raw0"], g["raw1"]], [g["inv_affine0"], g["inv_affine1"]], bb, dims, 1, fb, db)
+    assert np.array_equal(img, g["fused_img"]) and np.array_equal(w, g["fused_weight"])
+    assert np.array_equal(oracle.psf_average([g["psf_t0"], g["psf_t1"]]), g["psf_avg"])
+    assert np.array_equal(oracle.psf_make_same_size(g["psf_avg"], (25, 13, 17)), g["psf_same"])
+    raw_w = [g["blend0"], g["blend1"]]
+    for tag, osem, smooth in (("hard", 1.0, False), ("smooth", 1.0, True), ("osem", 2.0, False)):
+        for j, nw in enumerate(oracle.normalize_weights(raw_w, osem, smooth)):
+            assert np.array_equal(nw, g[f"norm_{tag}{j}"])
+
+
+def test_hostemu_reproduces_prep_golden(hostemu_lib, oracle, prep):
+    import mvrecon_b200 as m
+    g = prep
+    dims, bb, fb, db = _prep_inputs(g)
+    rv = [m.RawView(g[f"raw{j}"], g[f"inv_affine{j}"], 1, fb[j], db[j]) for j in range(2)]
+    dv = m.DeconViews([m.DeconView(m.FusedGroup(rv, bb, dims), None, np.ones((3, 3, 3), np.float32))], library=hostemu_lib)
+    try:
+        assert np.array_equal(dv.getImage(0), g["fused_img"]) and np.array_equal(dv.getWeight(0), g["fused_weight"])
+    finally:
+        dv.close()
+    t = [hostemu_lib.psf_transform(g[f"psf{j}"], g[f"affine{j}"], g[f"inv_affine{j}"]) for j in range(2)]
+    assert np.array_equal(t[0], g["psf_t0"]) and np.array_equal(t[1], g["psf_t1"])
+    assert np.array_equal(hostemu_lib.psf_average(t), g["psf_avg"])
+    assert np.array_equal(hostemu_lib.psf_make_same_size(g["psf_avg"], (25, 13, 17)), g["psf_same"])
+    dv = m.DeconViews([m.DeconView(np.ones(dims, np.float32), g[f"blend{j}"], np.ones((3, 3, 3), np.float32)) for j in range(2)], library=hostemu_lib)
+    try:
+        dv.normalizeWeights(1.0, True)
+        for j in range(2):
+            assert np.array_equal(dv.getWeight(j), g[f"norm_smooth{j}"])
+    finally:
+        dv.close()
