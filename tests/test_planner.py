@@ -33,7 +33,7 @@ def _check(lib, gdim, a, b, r1, r2, is_x, two, max_len):
     return T, tiles
 
 
-@settings(max_examples=300, deadline=None)
+@settings(max_examples=300, deadline=None, derandomize=True)
 @given(st.data())
 def test_plan_axis_properties(hostemu_lib, data):
     gdim = data.draw(st.integers(8, 3000))
@@ -61,7 +61,7 @@ def full_lib():
     return m.lib()
 
 
-@settings(max_examples=300, deadline=None)
+@settings(max_examples=300, deadline=None, derandomize=True)
 @given(st.data())
 def test_plan_axis_properties_all_lengths(full_lib, data):
     gdim = data.draw(st.integers(8, 6000))
