@@ -15,6 +15,7 @@
 #ifndef MVDECON_HPP
 #define MVDECON_HPP
 
+#include <algorithm>
 #include <array>
 #include <memory>
 #include <stdexcept>
@@ -290,6 +291,135 @@ class ComputeBlockSeqThreadB200Factory {                            // ComputeBl
     Dims blockSize_;
     std::vector<int> devices_;
 };
+
+// ---- block geometry of the reference (host logic) and the block-wise driver over the operator ---------------------------------------------
+// Block (M/process/cuda/Block.java:91-133,158-239), BlockGeneratorFixedSizePrecise.divideIntoBlocks (.../BlockGeneratorFixedSizePrecise.java:59-131),
+// BlockSorter.sortBlocksBySmallestFootprint (.../BlockSorter.java:55-143)
+struct Block {
+    Dims blockSize, offset, effectiveSize, effectiveOffset, effectiveLocalOffset;
+    int min(int d) const { return offset[(size_t)d]; }
+    // Block.copyBlock: cut [offset, offset + blockSize) out of `source`, extended by mirroring (extendMirrorSingle) or by zeros
+    void copyBlock(const float* source, const Dims& n, bool mirror, float* block) const {
+        auto map = [&](int c, int len, bool& out) {
+            out = c < 0 || c >= len;
+            if (!out || !mirror) return c;
+            if (len == 1) return 0;
+            const int period = 2 * (len - 1);
+            int m = c % period;
+            if (m < 0) m += period;
+            return m < len ? m : period - m;
+        };
+        for (int z = 0; z < blockSize[2]; ++z)
+            for (int y = 0; y < blockSize[1]; ++y)
+                for (int x = 0; x < blockSize[0]; ++x) {
+                    bool ox, oy, oz;
+                    const int sx = map(offset[0] + x, n[0], ox), sy = map(offset[1] + y, n[1], oy), sz = map(offset[2] + z, n[2], oz);
+                    const bool outside = ox || oy || oz;
+                    block[((size_t)z * blockSize[1] + y) * blockSize[0] + x] =
+                        (outside && !mirror) ? 0.f : source[((size_t)sz * n[1] + sy) * n[0] + sx];
+                }
+    }
+    // Block.pasteBlock: the effective region only
+    void pasteBlock(float* target, const Dims& n, const float* block) const {
+        for (int z = 0; z < effectiveSize[2]; ++z)
+            for (int y = 0; y < effectiveSize[1]; ++y)
+                for (int x = 0; x < effectiveSize[0]; ++x)
+                    target[((size_t)(effectiveOffset[2] + z) * n[1] + effectiveOffset[1] + y) * n[0] + effectiveOffset[0] + x] =
+                        block[((size_t)(effectiveLocalOffset[2] + z) * blockSize[1] + effectiveLocalOffset[1] + y) * blockSize[0] + effectiveLocalOffset[0] + x];
+    }
+};
+
+// empty result: the block is smaller than the kernel (the reference returns null)
+inline std::vector<Block> divideIntoBlocks(const Dims& imgSize, const Dims& blockSize, const Dims& kernelSize) {
+    Dims eff, loc, nb;
+    for (size_t d = 0; d < 3; ++d) {
+        eff[d] = blockSize[d] - kernelSize[d] + 1;
+        if (eff[d] <= 0) return {};
+        loc[d] = kernelSize[d] / 2;
+        nb[d] = (imgSize[d] + eff[d] - 1) / eff[d];
+    }
+    std::vector<Block> blocks;
+    for (int bz = 0; bz < nb[2]; ++bz)
+        for (int by = 0; by < nb[1]; ++by)
+            for (int bx = 0; bx < nb[0]; ++bx) {
+                const Dims cur{bx, by, bz};
+                Block b;
+                b.blockSize = blockSize; b.effectiveLocalOffset = loc;
+                for (size_t d = 0; d < 3; ++d) {
+                    b.effectiveOffset[d] = cur[d] * eff[d];
+                    b.effectiveSize[d] = std::min(eff[d], imgSize[d] - b.effectiveOffset[d]);
+                    b.offset[d] = b.effectiveOffset[d] - loc[d];
+                }
+                blocks.push_back(b);
+            }
+    return blocks;
+}
+
+inline std::vector<std::vector<Block>> sortBlocksBySmallestFootprint(const std::vector<Block>& blocks, const Dims& psiDims, int minRequiredBlocks = 1) {
+    const Dims eff = blocks.at(0).effectiveSize;
+    Dims nb;
+    for (size_t d = 0; d < 3; ++d) nb[d] = (psiDims[d] + eff[d] - 1) / eff[d];
+    std::vector<std::pair<long long, int>> sizes;              // (blocks per layer, dimension); a later dimension overwrites an equal size
+    for (int d = 0; d < 3; ++d) {
+        long long sz = 1;
+        for (int e = 0; e < 3; ++e) if (e != d) sz *= nb[(size_t)e];
+        sizes.emplace_back(sz, d);
+    }
+    auto dim_of = [&](long long sz) { int dim = -1; for (const auto& p : sizes) if (p.first == sz) dim = p.second; return dim; };
+    std::vector<long long> sorted{sizes[0].first, sizes[1].first, sizes[2].first};
+    std::sort(sorted.begin(), sorted.end());
+    int minDim = -1;
+    for (int i = 0; i < 3; ++i)
+        if (minDim == -1 && (sorted[(size_t)i] >= minRequiredBlocks || i == 2)) minDim = dim_of(sorted[(size_t)i]);
+    std::vector<std::vector<Block>> layers;
+    size_t total = 0;
+    for (int i = 0; i < nb[(size_t)minDim]; ++i) {
+        const int off = blocks[0].offset[(size_t)minDim] + i * eff[(size_t)minDim];
+        std::vector<Block> layer;
+        for (const Block& b : blocks) if (b.min(minDim) == off) layer.push_back(b);
+        total += layer.size();
+        layers.push_back(std::move(layer));
+    }
+    if (total != blocks.size()) return {blocks};
+    return layers;
+}
+
+// MultiViewDeconvolutionSeq.runNextIteration through the block operator (MultiViewDeconvolutionSeq.java:69-176): per view, batches of
+// non-interfering blocks, delayed paste-back of the effective regions.  psi is a caller-owned host volume, updated in place.
+inline std::vector<IterationStatistics> runNextIterationBlocked(float* psi, const Dims& dims, DeconViews& views, const std::vector<float>& maxIntensities,
+                                                                const ComputeBlockSeqThreadB200Factory& factory, const Dims& blockSize) {
+    ComputeBlockSeqThreadB200 worker = factory.create(0);
+    std::vector<IterationStatistics> out;
+    const size_t nblk = (size_t)numElements(blockSize);
+    std::vector<float> imgBlock(nblk), weightBlock(nblk);
+    for (size_t v = 0; v < views.getViews().size(); ++v) {
+        DeconView& view = views.getViews()[v];
+        const Dims k1d = view.getPSF().getKernel1Dims();
+        const Dims ksz{2 * k1d[0] - 1, 2 * k1d[1] - 1, 2 * k1d[2] - 1};         // DeconView.java:155-157
+        const std::vector<Block> blocks = divideIntoBlocks(dims, blockSize, ksz);
+        if (blocks.empty()) throw Error("block smaller than the kernel");
+        IterationStatistics st;
+        std::vector<std::pair<Block, std::vector<float>>> prev, cur;
+        for (const std::vector<Block>& batch : sortBlocksBySmallestFootprint(blocks, dims)) {
+            cur.clear();
+            for (const Block& blk : batch) {
+                blk.copyBlock(psi, dims, true, worker.getPsiBlockTmp().data());
+                blk.copyBlock(view.getImage().data, dims, false, imgBlock.data());
+                blk.copyBlock(view.getWeight().data, dims, false, weightBlock.data());
+                const IterationStatistics s = worker.runIteration(imgBlock.data(), weightBlock.data(), maxIntensities.at(v), view.getPSF());
+                st.sumChange += s.sumChange;
+                st.maxChange = std::max(st.maxChange, s.maxChange);
+                if (blocks.size() == 1) blk.pasteBlock(psi, dims, worker.getPsiBlockTmp().data());
+                else cur.emplace_back(blk, worker.getPsiBlockTmp());
+            }
+            for (const auto& p : prev) p.first.pasteBlock(psi, dims, p.second.data());
+            prev.swap(cur);
+        }
+        for (const auto& p : prev) p.first.pasteBlock(psi, dims, p.second.data());
+        out.push_back(st);
+    }
+    return out;
+}
 
 }  // namespace mvrecon
 #endif  // MVDECON_HPP

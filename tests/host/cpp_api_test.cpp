@@ -75,6 +75,19 @@ int main(int argc, char** argv) {
         const IterationStatistics bs = worker.runIteration(img[0].data(), w[0].data(), mx[0], views.getViews()[0].getPSF());
         write_f32(dir + "/block_out.f32", worker.getPsiBlockTmp());
         st << bs.sumChange << " " << bs.maxChange << "\n";
+
+        // block-wise driver: halo'd blocks of 16^3 through the operator, delayed paste-back, one iteration from psi0
+        std::vector<float> psi = psi0;
+        const Dims bsz{16, 16, 16};
+        ComputeBlockSeqThreadB200Factory bf(MultiViewDeconvolution::minValue, lambda, bsz, {0});
+        const Dims k1d = views.getViews()[0].getPSF().getKernel1Dims();
+        const std::vector<Block> blocks = divideIntoBlocks(dims, bsz, Dims{2 * k1d[0] - 1, 2 * k1d[1] - 1, 2 * k1d[2] - 1});
+        if (blocks.size() < 8) throw Error("expected a multi-block plan");
+        size_t covered = 0;
+        for (const Block& b : blocks) covered += (size_t)numElements(b.effectiveSize);
+        if ((long long)covered != numElements(dims)) throw Error("effective regions do not tile the volume");
+        for (const IterationStatistics& s : runNextIterationBlocked(psi.data(), dims, views, mx, bf, bsz)) st << s.sumChange << " " << s.maxChange << "\n";
+        write_f32(dir + "/psi_blocked.f32", psi);
     } catch (const std::exception& e) {
         std::cerr << "cpp_api_test: " << e.what() << "\n";
         return 1;

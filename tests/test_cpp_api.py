@@ -34,10 +34,14 @@ def test_cpp_mirror_runs_the_loop(hostemu_lib, oracle, tmp_path):
     got = np.fromfile(tmp_path / "psi_out.f32", np.float32).reshape(dims)
     assert oracle.rel_l2(got, ref) < 4e-6
     lines = [tuple(float(x) for x in l.split()) for l in open(tmp_path / "stats.txt").read().splitlines()]
-    assert len(lines) == iters * V + 1
-    for (s, m), (_, _, ws, wm) in zip(lines[:-1], stats):
+    assert len(lines) == iters * V + 1 + V
+    for (s, m), (_, _, ws, wm) in zip(lines[:iters * V], stats):
         assert abs(s - ws) <= 1e-4 * max(1.0, abs(ws)) + 1e-2 and abs(m - wm) <= 1e-4 * max(1.0, abs(wm))
     # block operator on the whole volume as one block = one whole-volume update of view 0 (mirror / constant-1 extension)
     one, s0, m0 = oracle.view_update_whole(psi0, views[0], lam, dtype=np.float64)
     blk = np.fromfile(tmp_path / "block_out.f32", np.float32).reshape(dims)
     assert oracle.rel_l2(blk, one) < 2e-6
+    # the block-wise driver over the operator (16^3 halo'd blocks, delayed paste-back) equals the whole-volume iteration
+    one_it, _ = oracle.run_iterations_seq(psi0, views, 1, lam, dtype=np.float64)
+    blocked = np.fromfile(tmp_path / "psi_blocked.f32", np.float32).reshape(dims)
+    assert oracle.rel_l2(blocked, one_it) < 4e-6
