@@ -80,7 +80,10 @@ typedef struct mvd_config {
     /* AdjustInput.sumImg adds sums[0] and then loops over ALL portion sums including index 0 (AdjustInput.java:115-119), i.e. the
      * first portion (first floor(size/numPortions) samples, numPortions = max(T, size/64^3), T = max(4, #threads),
      * FusionTools.java:1287-1329, Threads.java:40) is counted twice, so the reference's "normalised" kernels do not sum to 1 and
-     * the result depends on the thread count.  0 = exact sum (default); T > 0 reproduces the reference run with T ImageJ threads. */
+     * the result depends on the thread count.  The default reproduces the reference: 0 = the reference run on THIS host, i.e.
+     * T = mvd_reference_threads() = max(4, processors); T > 0 = the reference run with T ImageJ threads (the Java glue passes
+     * Threads.numThreads()); < 0 = exact sums (what the author intended; opt-in, differs from the reference by up to ~1 % in the
+     * kernel scale and a few percent in psi after 10 iterations on small PSFs).                                                    */
     int norm_quirk_threads;
     /* optional second sharding axis (y), same meaning as the z fields; all zero = y is not sharded.  A 2-d (y x z) process grid keeps the
      * redundant halo volume small: the single-GPU plan already splits y into two FFT tiles, so a 2-way y split costs nothing.            */
@@ -96,6 +99,9 @@ typedef struct mvd_config {
 
 MVD_API const char* mvd_last_error(void);                     /* thread-local message of the last failing call          */
 MVD_API int mvd_version(void);
+/* Threads.numThreads() of this host as the library sees it: max(4, processors) (M/Threads.java:40) -- the T that
+ * mvd_config.norm_quirk_threads == 0 stands for.                                                                        */
+MVD_API int mvd_reference_threads(void);
 /* FFT tile lengths compiled into the library (ascending, all 2^a 3^b 5^c); returns the count, fills at most cap entries.              */
 MVD_API int mvd_supported_fft_lengths(int* out, int cap);
 

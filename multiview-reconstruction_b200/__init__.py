@@ -89,6 +89,7 @@ SYMBOLS = {
     "getFreeMemDeviceCUDA": (C.c_longlong, [C.c_int]),
     "mvd_last_error": (C.c_char_p, []),
     "mvd_version": (C.c_int, []),
+    "mvd_reference_threads": (C.c_int, []),
     "mvd_supported_fft_lengths": (C.c_int, [_I, C.c_int]),
     "mvd_create": (C.c_int, [C.POINTER(_Config), C.POINTER(C.c_void_p)]),
     "mvd_destroy": (C.c_int, [C.c_void_p]),
@@ -477,7 +478,9 @@ class DeconViews:
         if shard_y is not None:
             cfg.shard_y_lo, cfg.shard_y_hi, cfg.local_y0, cfg.local_ny = (int(x) for x in shard_y)
         cfg.max_fft_len = int(max_fft_len)
-        cfg.norm_quirk_threads = int(norm_quirk_threads)      # 0 = exact sums; T reproduces AdjustInput.sumImg for T threads
+        # AdjustInput.sumImg's double count (AdjustInput.java:115-119): 0 = like the reference on this host (Threads.numThreads()),
+        # T > 0 = like a reference run with T threads, -1 = exact sums (opt-in; NOT what the reference computes)
+        cfg.norm_quirk_threads = int(norm_quirk_threads)
         cfg.exchange_scheme = int(exchange_scheme)            # sharded contexts: 0 = psi exchange only, 1 = psi + quotient exchange
         self._ctx = C.c_void_p()
         self.lib.check(self.lib.dll.mvd_create(C.byref(cfg), C.byref(self._ctx)))

@@ -8,6 +8,9 @@
 
 #include "engine.h"
 
+#include <algorithm>
+#include <thread>
+
 using namespace mvd;
 
 struct mvd_comm { std::shared_ptr<NcclComm> comm; };
@@ -50,7 +53,11 @@ void require_device(int) {}
 extern "C" {
 
 const char* mvd_last_error(void) { return g_last_error.c_str(); }
-int mvd_version(void) { return 100; }
+int mvd_version(void) { return 200; }
+int mvd_reference_threads(void) {        // Threads.numThreads() = max(4, Prefs.getThreads()), ImageJ's default = processors (Threads.java:40)
+    const unsigned n = std::thread::hardware_concurrency();
+    return (int)std::max(4u, n);
+}
 int mvd_supported_fft_lengths(int* out, int cap) {
     const std::vector<int>& v = supported_lengths();
     for (int i = 0; i < (int)v.size() && i < cap && out; ++i) out[i] = v[i];
@@ -68,7 +75,8 @@ int mvd_create(const mvd_config* cfg, mvd_context** out) {
         c.lambda = cfg->lambda;
         c.min_value = cfg->min_value;
         c.max_len = cfg->max_fft_len > 0 ? cfg->max_fft_len : 1152;
-        c.norm_quirk_threads = cfg->norm_quirk_threads > 0 ? cfg->norm_quirk_threads : 0;
+        // 0 = what the reference does on this host (Threads.numThreads()), T > 0 = a reference run with T threads, < 0 = exact sums
+        c.norm_quirk_threads = cfg->norm_quirk_threads > 0 ? cfg->norm_quirk_threads : (cfg->norm_quirk_threads < 0 ? 0 : mvd_reference_threads());
         require(cfg->exchange_scheme == 0 || cfg->exchange_scheme == 1, "exchange_scheme must be 0 or 1");
         c.exchange_scheme = cfg->exchange_scheme;
         require(cfg->psf_type >= 0 && cfg->psf_type <= 3, "bad psf_type");

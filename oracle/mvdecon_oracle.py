@@ -91,24 +91,31 @@ def divide_into_portions(image_size: int, threads: Optional[int] = None) -> List
 # --------------------------------------------------------------------------------------
 # AdjustInput.sumImg / normToSum1   (M/process/deconvolution/normalization/AdjustInput.java:52-122)
 # --------------------------------------------------------------------------------------
-def sum_img(img: np.ndarray, quirk_threads: Optional[int] = None) -> float:
-    """Sum of all pixels in float64 (RealSum).
+REFERENCE_THREADS = "reference"      # quirk_threads value: the run-time default of the reference, Threads.numThreads() of this host
 
-    quirk_threads=None  -> exact sum (oracle default policy, SURVEY 8a-6 'Quirk A').
-    quirk_threads=T     -> reproduces AdjustInput.java:115-119: ``sum.add(sums[0])`` followed
-                           by a loop over *all* sums including index 0, i.e. portion 0 (first
-                           floor(size/numPortions) pixels in x-fastest order) counted twice,
-                           for Threads.numThreads() == max(4, T).
+
+def sum_img(img: np.ndarray, quirk_threads=REFERENCE_THREADS) -> float:
+    """Sum of all pixels in float64 (RealSum) the way AdjustInput.sumImg computes it.
+
+    quirk_threads=REFERENCE_THREADS (default) or T
+                        -> AdjustInput.java:115-119 as written: ``sum.add(sums[0])`` followed by a loop over
+                           *all* sums including index 0, i.e. portion 0 (first floor(size/numPortions) pixels in
+                           x-fastest order; sums[] is filled in task start order, portion 0 being the first task
+                           submitted) is counted twice, for Threads.numThreads() == max(4, T)
+                           (T = the host's processor count for REFERENCE_THREADS).  SURVEY 8a-6 'Quirk A'.
+    quirk_threads=None  -> exact sum (what the author intended; opt-in, not the reference's behaviour).
     """
     flat = np.asarray(img, dtype=np.float64).ravel()  # C order of [z,y,x] == x fastest
     total = math.fsum(flat.tolist()) if flat.size <= 1 << 20 else float(flat.sum(dtype=np.float64))
     if quirk_threads is not None:
+        if quirk_threads == REFERENCE_THREADS:
+            quirk_threads = None                       # num_threads(None) = max(4, processors)
         start, loop = divide_into_portions(flat.size, quirk_threads)[0]
         total += float(flat[start:start + loop].sum(dtype=np.float64))
     return total
 
 
-def norm_to_sum1(img: np.ndarray, quirk_threads: Optional[int] = None) -> np.ndarray:
+def norm_to_sum1(img: np.ndarray, quirk_threads=REFERENCE_THREADS) -> np.ndarray:
     """t = (float)((double)t / sum)   (AdjustInput.java:52-58). Returns a new float32 array."""
     s = sum_img(img, quirk_threads)
     return (np.asarray(img, dtype=np.float32).astype(np.float64) / s).astype(np.float32)
@@ -244,7 +251,7 @@ def direct_convolve(img: np.ndarray, kernel: np.ndarray, ext: str = "mirror", co
 # --------------------------------------------------------------------------------------
 # DeconViewPSF.init   (M/process/deconvolution/DeconViewPSF.java:119-254)
 # --------------------------------------------------------------------------------------
-def derive_kernels(psfs: Sequence[np.ndarray], psf_type: int, quirk_threads: Optional[int] = None,
+def derive_kernels(psfs: Sequence[np.ndarray], psf_type: int, quirk_threads=REFERENCE_THREADS,
                    dtype=np.float32) -> Tuple[List[np.ndarray], List[np.ndarray]]:
     """Returns (kernel1[], kernel2[]) exactly in the order DeconViews calls psf.init
     (M/process/deconvolution/DeconViews.java:69-70): view v's kernel1 is normalised at the
@@ -1106,7 +1113,7 @@ def make_synthetic(dims_zyx, num_views: int, seed: int, psf_size_xyz=(25, 19, 25
     return SynthDataset(tuple(dims_zyx), psfs, images, weights, truth, boxes)
 
 
-def make_oracle_views(ds: SynthDataset, psf_type: int, quirk_threads: Optional[int] = None):
+def make_oracle_views(ds: SynthDataset, psf_type: int, quirk_threads=REFERENCE_THREADS):
     """kernels by PSFTYPE, psi0 / max[] by FUSED_BLURRED.  Returns (views, psi0, avg)."""
     k1, k2 = derive_kernels(ds.psfs, psf_type, quirk_threads)
     psi0, mx, avg = psi_init_blurred_fused(ds.images, ds.weights)

@@ -26,7 +26,8 @@ def test_product_library_exports_every_declared_symbol():
     dll = ctypes.CDLL(m.LIBRARY_PATH)
     for name in _declared_symbols():
         assert hasattr(dll, name), name
-    assert dll.mvd_version() >= 100
+    assert dll.mvd_version() >= 200
+    assert dll.mvd_reference_threads() == max(4, os.cpu_count() or 1)
 
 
 def test_no_cpu_fallback_without_device():

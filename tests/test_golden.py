@@ -41,7 +41,7 @@ def test_oracle_float32_reproduces_golden(oracle, gold):
 def test_kernel_derivation_reproduces_golden(oracle, gold):
     psfs = [gold[f"psf{v}"] for v in range(3)]
     for ptype in range(4):
-        k1, k2 = oracle.derive_kernels(psfs, ptype)
+        k1, k2 = oracle.derive_kernels(psfs, ptype, quirk_threads=int(gold["quirk_threads"]))
         for v in range(3):
             assert oracle.rel_l2(k1[v], gold[f"k1_t{ptype}_v{v}"]) < 1e-6
             assert oracle.rel_l2(k2[v], gold[f"k2_t{ptype}_v{v}"]) < 2e-6
@@ -50,7 +50,7 @@ def test_kernel_derivation_reproduces_golden(oracle, gold):
 def test_hostemu_reproduces_golden(hostemu_lib, oracle, gold):
     import mvrecon_b200 as m
     views = [m.DeconView(gold[f"img{v}"], gold[f"weight{v}"], gold[f"psf{v}"], m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(3)]
-    dv = m.DeconViews(views, lambda_=float(gold["lambda"]), library=hostemu_lib)
+    dv = m.DeconViews(views, lambda_=float(gold["lambda"]), norm_quirk_threads=int(gold["quirk_threads"]), library=hostemu_lib)
     try:
         dec = m.MultiViewDeconvolutionSeq(dv, 5, m.PsiInitFromRAI(gold["psi0"], gold["max"]))
         k = 0

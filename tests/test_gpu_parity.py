@@ -98,7 +98,7 @@ def test_golden_vectors(product_lib, oracle):
     import mvrecon_b200 as m
     gold = np.load(GOLD)
     views = [m.DeconView(gold[f"img{v}"], gold[f"weight{v}"], gold[f"psf{v}"], m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(3)]
-    dv = m.DeconViews(views, lambda_=float(gold["lambda"]))
+    dv = m.DeconViews(views, lambda_=float(gold["lambda"]), norm_quirk_threads=int(gold["quirk_threads"]))
     try:
         for ptype in (2,):
             for v in range(3):
@@ -125,7 +125,7 @@ def test_golden_kernels_all_psf_types(product_lib, oracle, ptype):
     import mvrecon_b200 as m
     gold = np.load(GOLD)
     views = [m.DeconView(gold[f"img{v}"], gold[f"weight{v}"], gold[f"psf{v}"], m.PSFTYPE(ptype)) for v in range(3)]
-    dv = m.DeconViews(views)
+    dv = m.DeconViews(views, norm_quirk_threads=int(gold["quirk_threads"]))
     try:
         for v in range(3):
             assert oracle.rel_l2(dv.views[v].psf.getKernel1(), gold[f"k1_t{ptype}_v{v}"]) < 1e-6
@@ -134,11 +134,17 @@ def test_golden_kernels_all_psf_types(product_lib, oracle, ptype):
         dv.close()
 
 
-def test_norm_quirk_switch(product_lib, oracle, small_dataset):
+@pytest.mark.parametrize("lib_t,ora_t", [(0, "reference"), (8, 8), (-1, None)])
+def test_norm_quirk_switch(product_lib, oracle, small_dataset, lib_t, ora_t):
+    """AdjustInput.sumImg's double count (AdjustInput.java:115-119): the library DEFAULT (0) is the reference's behaviour on this host
+    (T = Threads.numThreads()), T > 0 a reference run with T threads, -1 the exact sums; each against the oracle's same switch."""
     import mvrecon_b200 as m
-    views, psi0, avg = oracle.make_oracle_views(small_dataset, oracle.EFFICIENT_BAYESIAN, quirk_threads=8)
-    dv = m.DeconViews(_views(m, small_dataset, 2), lambda_=0.006, norm_quirk_threads=8)
+    assert product_lib.dll.mvd_reference_threads() == oracle.num_threads()
+    views, psi0, avg = oracle.make_oracle_views(small_dataset, oracle.EFFICIENT_BAYESIAN, quirk_threads=ora_t)
+    dv = m.DeconViews(_views(m, small_dataset, 2), lambda_=0.006, norm_quirk_threads=lib_t)
     try:
+        for v in range(3):
+            assert oracle.rel_l2(dv.views[v].psf.getKernel1(), views[v].kernel1) < 1e-6
         dec = m.MultiViewDeconvolutionSeq(dv, 3, m.PsiInitFromRAI(psi0, [v.max_intensity for v in views]))
         dec.runIterations()
         ref, _ = oracle.run_iterations_seq(psi0, views, 3, 0.006, dtype=np.float64)

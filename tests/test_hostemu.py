@@ -59,15 +59,22 @@ def test_norm_quirk_switch_matches_oracle(hostemu_lib, oracle, small_dataset):
     """mvd_config.norm_quirk_threads reproduces AdjustInput.sumImg's double count exactly like the oracle's switch."""
     import mvrecon_b200 as m
     ds = small_dataset
-    views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN, quirk_threads=8)
-    dv = m.DeconViews(_views(m, ds, 2), norm_quirk_threads=8, library=hostemu_lib)
-    try:
-        for v in range(3):
-            assert abs(float(dv.views[v].psf.getKernel1().sum(dtype=np.float64)) - float(views[v].kernel1.sum(dtype=np.float64))) < 1e-6
-            assert oracle.rel_l2(dv.views[v].psf.getKernel1(), views[v].kernel1) < 1e-6
-            assert oracle.rel_l2(dv.views[v].psf.getKernel2(), views[v].kernel2) < 2e-6
-    finally:
-        dv.close()
+    assert hostemu_lib.dll.mvd_reference_threads() == oracle.num_threads()
+    # (library setting, oracle setting): the DEFAULT of both is the reference's own behaviour on this host; -1 / None = exact sums
+    for lib_t, ora_t in ((0, oracle.REFERENCE_THREADS), (8, 8), (5, 5), (-1, None)):
+        views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN, quirk_threads=ora_t)
+        dv = m.DeconViews(_views(m, ds, 2), norm_quirk_threads=lib_t, library=hostemu_lib)
+        try:
+            for v in range(3):
+                assert abs(float(dv.views[v].psf.getKernel1().sum(dtype=np.float64)) - float(views[v].kernel1.sum(dtype=np.float64))) < 1e-6
+                assert oracle.rel_l2(dv.views[v].psf.getKernel1(), views[v].kernel1) < 1e-6
+                assert oracle.rel_l2(dv.views[v].psf.getKernel2(), views[v].kernel2) < 2e-6
+            if lib_t == -1:
+                assert abs(float(dv.views[0].psf.getKernel1().sum(dtype=np.float64)) - 1.0) < 1e-6
+            else:
+                assert abs(float(dv.views[0].psf.getKernel1().sum(dtype=np.float64)) - 1.0) > 1e-4        # the reference's kernels do NOT sum to 1
+        finally:
+            dv.close()
 
 
 def test_multitile_equals_single_tile(hostemu_lib, oracle):

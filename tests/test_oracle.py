@@ -30,7 +30,7 @@ def test_fft_convolve_equals_direct(oracle, ext):
 
 
 def test_constant_psi_stays_constant_under_normalised_kernel(oracle):
-    k = oracle.norm_to_sum1(np.random.default_rng(2).random((5, 5, 5)).astype(np.float32))
+    k = oracle.norm_to_sum1(np.random.default_rng(2).random((5, 5, 5)).astype(np.float32), quirk_threads=None)     # exact sum
     psi = np.full((12, 11, 10), 3.5, np.float32)
     blur = oracle.fft_convolve(psi, k, "mirror", dtype=np.float64)
     assert np.abs(blur - 3.5).max() < 1e-5          # sum K == 1 up to float32 rounding of the normalised taps
@@ -74,7 +74,7 @@ def test_statistics_are_signed(oracle):
 def test_img_equals_blur_leaves_psi_unchanged(oracle):
     rng = np.random.default_rng(3)
     psi = (1 + rng.random((10, 9, 8))).astype(np.float32)
-    k = oracle.norm_to_sum1(rng.random((3, 3, 3)).astype(np.float32))
+    k = oracle.norm_to_sum1(rng.random((3, 3, 3)).astype(np.float32), quirk_threads=None)
     img = oracle.fft_convolve(psi, k, "mirror", dtype=np.float32)
     v = oracle.OracleView(img, np.ones_like(psi), k, oracle.compute_inverted_kernel(k), 1.0)
     nxt, s, m = oracle.view_update_whole(psi, v, 0.0, dtype=np.float32)
@@ -121,15 +121,18 @@ def test_mirror_quirk_even_sizes(oracle):
 
 def test_sum_quirk_double_counts_first_portion(oracle):
     k = np.arange(1, 1001, dtype=np.float32).reshape(10, 10, 10)
-    exact = oracle.sum_img(k)
+    exact = oracle.sum_img(k, quirk_threads=None)
     assert exact == 500500.0
+    # the default is the reference's behaviour on this host: Threads.numThreads() = max(4, processors)
+    s0, l0 = oracle.divide_into_portions(k.size, None)[0]
+    assert oracle.sum_img(k) == exact + float(k.ravel()[s0:s0 + l0].sum())
     T = 8
     start, loop = oracle.divide_into_portions(k.size, T)[0]
     assert oracle.sum_img(k, quirk_threads=T) == exact + float(k.ravel()[start:start + loop].sum())
     # the effect on a PSF-like kernel is NOT negligible (SURVEY 8a-6 underestimates it): 0.77 % for this 25x19x25 PSF at T = 8,
     # which is why the engine exposes the same switch (mvd_config.norm_quirk_threads) instead of ignoring the quirk
     psf = oracle.synth_psf(0, 4)
-    a, b = oracle.norm_to_sum1(psf), oracle.norm_to_sum1(psf, quirk_threads=8)
+    a, b = oracle.norm_to_sum1(psf, quirk_threads=None), oracle.norm_to_sum1(psf, quirk_threads=8)
     assert 1e-3 < oracle.rel_l2(b, a) < 2e-2
 
 
@@ -145,11 +148,17 @@ def test_portions(oracle):
 def test_kernel_derivation_properties(oracle):
     psfs = [oracle.synth_psf(v, 3, (7, 5, 7), (1.2, 1.0, 2.0)) * (v + 2) for v in range(3)]
     for ptype in range(4):
-        k1, k2 = oracle.derive_kernels(psfs, ptype)
+        k1, k2 = oracle.derive_kernels(psfs, ptype, quirk_threads=None)          # exact sums: kernels sum to 1
         for a, b in zip(k1, k2):
             assert abs(float(a.sum(dtype=np.float64)) - 1) < 1e-5
             if ptype != oracle.INDEPENDENT:
                 assert abs(float(b.sum(dtype=np.float64)) - 1) < 1e-5
+        # the reference's kernels (default) are scaled by sum / (sum + first portion): strictly below 1 for positive PSFs
+        q1, q2 = oracle.derive_kernels(psfs, ptype)
+        for a, qa in zip(k1, q1):
+            start, loop = oracle.divide_into_portions(a.size, None)[0]
+            assert float(qa.sum(dtype=np.float64)) < 1 - 1e-6
+            assert oracle.rel_l2(qa * (1.0 + float(a.ravel()[start:start + loop].sum(dtype=np.float64))), a) < 1e-6
     k1, k2 = oracle.derive_kernels(psfs, oracle.INDEPENDENT)
     assert np.array_equal(k2[0], k1[0][::-1, ::-1, ::-1])
     k1, k2 = oracle.derive_kernels(psfs[:1], oracle.EFFICIENT_BAYESIAN)       # a single view falls back to the flipped kernel
