@@ -110,7 +110,8 @@ MVD_API int mvd_destroy(mvd_context* ctx);
 
 /* DeconView: observed image (0 where the view has no data, MultiViewDeconvolution.outsideValueImg) and weight volume of
  * view v; local array size dims[0]*dims[1]*local_nz.  _host copies host->device, _device borrows caller-owned device
- * memory that must stay valid until mvd_destroy.                                                                       */
+ * memory that must stay valid until mvd_destroy.  weight == NULL (all three variants): the context allocates the weight
+ * volume itself, to be filled on the device by mvd_make_blending_weights* + mvd_normalize_weights ("virtual" weights).   */
 MVD_API int mvd_set_view(mvd_context* ctx, int v, const float* img_host, const float* weight_host);
 MVD_API int mvd_set_view_device(mvd_context* ctx, int v, const float* img_dev, const float* weight_dev);
 /* Asynchronous variant of mvd_set_view: the copies are enqueued on a separate copy stream and the call returns immediately; the host
@@ -257,6 +258,13 @@ typedef struct mvd_halo_box {
 } mvd_halo_box;
 typedef int (*mvd_exchange_fn)(void* user, int which, const mvd_halo_box* box);
 MVD_API int mvd_set_exchange_callback(mvd_context* ctx, mvd_exchange_fn fn, void* user);
+/* Global quantities of a sharded job -- the per-view maxima and the average of PsiInit (MultiViewDeconvolution.java:115-135), the
+ * IterationStatistics of a view update over all blocks (MultiViewDeconvolutionSeq.java:165-176) -- are all-reduced over the attached
+ * communicator (ncclAllReduce), or through this host callback when the host brings its own plumbing: reduce values[0..count) in place
+ * over all ranks, op 0 = sum, 1 = max; return 0 on success.  Calls that return such quantities (mvd_psi_init, mvd_psi_init_from_file,
+ * mvd_run_iterations with stats, mvd_run_view_update with stats, mvd_fetch_stats) are collective on a sharded context.               */
+typedef int (*mvd_reduce_fn)(void* user, double* values, int count, int op);
+MVD_API int mvd_set_reduce_callback(mvd_context* ctx, mvd_reduce_fn fn, void* user);
 
 /* Per-pass device timing (CUDA events on the context's stream around every pass launch): slots 0..8 = passes P1..P9 of a
  * view update.  ms[] are accumulated milliseconds, counts[] the number of launches; reset != 0 clears them.   */

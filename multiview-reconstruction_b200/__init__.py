@@ -64,6 +64,7 @@ class HaloBox(C.Structure):
 
 
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(HaloBox))
+REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_int)
 
 
 class _RawView(C.Structure):
@@ -126,6 +127,7 @@ SYMBOLS = {
     "mvd_comm_destroy": (C.c_int, [C.c_void_p]),
     "mvd_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mvd_set_exchange_callback": (C.c_int, [C.c_void_p, EXCHANGE_FN, C.c_void_p]),
+    "mvd_set_reduce_callback": (C.c_int, [C.c_void_p, REDUCE_FN, C.c_void_p]),
     "mvd_exchange_transport": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "mvd_psi_init_from_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, _D, _F]),
     "mvd_tiff_dims": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
@@ -493,9 +495,10 @@ class DeconViews:
                     self.lib.check(self.lib.dll.mvd_fuse_group(self._ctx, i, g._records(), len(g.raw_views), _i3(g.bbox_min),
                                                                g.min_value_img, g.outside_value))
                 elif isinstance(v.image, DeviceArray) or isinstance(v.weight, DeviceArray):
-                    if not (isinstance(v.image, DeviceArray) and isinstance(v.weight, DeviceArray)):
+                    if not (isinstance(v.image, DeviceArray) and (v.weight is None or isinstance(v.weight, DeviceArray))):
                         raise MvdError("image and weight of a view must both be host arrays or both DeviceArrays")
-                    self.lib.check(self.lib.dll.mvd_set_view_device(self._ctx, i, C.c_void_p(v.image.ptr), C.c_void_p(v.weight.ptr)))
+                    self.lib.check(self.lib.dll.mvd_set_view_device(self._ctx, i, C.c_void_p(v.image.ptr),
+                                                                    None if v.weight is None else C.c_void_p(v.weight.ptr)))
                 elif async_upload:      # this object keeps the host arrays alive until close(); page-locked arrays overlap with compute
                     self.lib.check(self.lib.dll.mvd_set_view_async(self._ctx, i, _fp(v.image), None if v.weight is None else _fp(v.weight)))
                 elif v.weight is None:
@@ -604,6 +607,20 @@ class DeconViews:
                 return 1
         self._exchange_cb = EXCHANGE_FN(tramp)                # keep the trampoline alive as long as the context
         self.lib.check(self.lib.dll.mvd_set_exchange_callback(self._ctx, self._exchange_cb, None))
+
+    def set_reduce_callback(self, fn):
+        """host-provided all-reduce of the job's global quantities (per-view maxima, PsiInit average, iteration statistics):
+        fn(values: float64 numpy array, op) reduces in place over all ranks, op 0 = sum, 1 = max"""
+        def tramp(_user, values, count, op):
+            try:
+                fn(np.ctypeslib.as_array(values, shape=(int(count),)), int(op))
+                return 0
+            except Exception:  # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._reduce_cb = REDUCE_FN(tramp)
+        self.lib.check(self.lib.dll.mvd_set_reduce_callback(self._ctx, self._reduce_cb, None))
 
     def exchange_halos(self):
         self.lib.check(self.lib.dll.mvd_exchange_halos(self._ctx))

@@ -112,7 +112,7 @@ int mvd_set_view_async(mvd_context* ctx, int v, const float* img, const float* w
     return guarded([&] { require(ctx && img, "null argument"); ctx->engine->set_view_host_async(v, img, weight); });
 }
 int mvd_set_view_device(mvd_context* ctx, int v, const float* img, const float* weight) {
-    return guarded([&] { require(ctx && img && weight, "null argument"); ctx->engine->set_view_device(v, img, weight); });
+    return guarded([&] { require(ctx && img, "null argument"); ctx->engine->set_view_device(v, img, weight); });
 }
 int mvd_set_psf(mvd_context* ctx, int v, const float* psf, const int kdims[3]) {
     return guarded([&] {
@@ -271,6 +271,9 @@ int mvd_set_exchange_callback(mvd_context* ctx, mvd_exchange_fn fn, void* user) 
         require(ctx != nullptr, "null argument");
         ctx->engine->set_exchange_callback(reinterpret_cast<ExchangeFn>(fn), user);
     });
+}
+int mvd_set_reduce_callback(mvd_context* ctx, mvd_reduce_fn fn, void* user) {
+    return guarded([&] { require(ctx != nullptr, "null argument"); ctx->engine->set_reduce_callback(reinterpret_cast<ReduceFn>(fn), user); });
 }
 static_assert(sizeof(mvd_raw_view) == sizeof(RawViewDev), "mvd_raw_view mirrors RawViewDev");
 int mvd_fuse_group(mvd_context* ctx, int v, const mvd_raw_view* views, int count, const int bbox_min[3], float min_value_img,

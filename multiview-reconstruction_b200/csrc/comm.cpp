@@ -29,6 +29,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi& nccl() {
@@ -43,14 +44,14 @@ NcclApi& nccl() {
 #define MVD_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, name)); if (!api.field) throw Error("NCCL symbol missing: " name);
     MVD_SYM(GetUniqueId, "ncclGetUniqueId") MVD_SYM(CommInitRank, "ncclCommInitRank") MVD_SYM(CommDestroy, "ncclCommDestroy")
     MVD_SYM(GroupStart, "ncclGroupStart") MVD_SYM(GroupEnd, "ncclGroupEnd") MVD_SYM(Send, "ncclSend") MVD_SYM(Recv, "ncclRecv")
-    MVD_SYM(GetErrorString, "ncclGetErrorString") MVD_SYM(AllGather, "ncclAllGather")
+    MVD_SYM(GetErrorString, "ncclGetErrorString") MVD_SYM(AllGather, "ncclAllGather") MVD_SYM(AllReduce, "ncclAllReduce")
 #undef MVD_SYM
     return api;
 }
 void nccl_check(ncclResult_t r, const char* what) {
     if (r != 0) throw Error(std::string("NCCL ") + what + ": " + nccl().GetErrorString(r));
 }
-constexpr int kNcclFloat = 7, kNcclChar = 0;
+constexpr int kNcclFloat = 7, kNcclChar = 0, kNcclDouble = 8, kNcclSum = 0, kNcclMax = 2;
 }  // namespace
 
 #endif
@@ -120,6 +121,7 @@ HaloComm::HaloComm(std::shared_ptr<NcclComm> comm, int py, int pz, stream_t s, s
 
 HaloComm::~HaloComm() {
     for (float* p : stage_) dev::free_(p);
+    dev::free_(red_dev_);
     close_peer();
 }
 
@@ -137,10 +139,30 @@ static void check_box(const HaloBox& b, bool ylower, bool yupper, bool zlower, b
         throw Error("halo exchange: the array does not contain the halo planes");
 }
 
-void HaloComm::exchange(const HaloBox& b) {
+void HaloComm::exchange(const HaloBox& b, bool force_nccl) {
     const bool ydo = py_ > 1 && (b.hy_lo > 0 || b.hy_hi > 0), zdo = pz_ > 1 && (b.hz_lo > 0 || b.hz_hi > 0);
     check_box(b, ydo && ry_ > 0, ydo && ry_ < py_ - 1, zdo && rz_ > 0, zdo && rz_ < pz_ - 1);
-    if (peer_) exchange_peer(b); else exchange_nccl(b);
+    if (peer_ && !force_nccl) exchange_peer(b); else exchange_nccl(b);
+}
+
+void HaloComm::all_reduce(double* host_values, int count, int op) {
+#ifndef MVD_HOST_EMU
+    if (count <= 0) return;
+    if ((size_t)count > red_cap_) {
+        dev::sync(stream_);
+        dev::free_(red_dev_);
+        red_cap_ = std::max((size_t)count, (size_t)256);
+        red_dev_ = (double*)dev::alloc(sizeof(double) * red_cap_);
+    }
+    dev::h2d(red_dev_, host_values, sizeof(double) * (size_t)count, stream_);
+    nccl_check(nccl().AllReduce(red_dev_, red_dev_, (size_t)count, kNcclDouble, op == 1 ? kNcclMax : kNcclSum, (ncclComm_t)comm_->raw(), stream_),
+               "allreduce");
+    dev::d2h(host_values, red_dev_, sizeof(double) * (size_t)count, stream_);
+    dev::sync(stream_);
+#else
+    (void)host_values; (void)count; (void)op;
+    throw Error("the host emulator has no NCCL");
+#endif
 }
 
 // Neighbour below (ry-1 / rz-1): it needs my first h*_hi own rows / planes (its upper halo) and sends its last h*_lo ones (my lower

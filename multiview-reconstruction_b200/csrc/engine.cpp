@@ -476,12 +476,15 @@ void Engine::set_view_host(int v, const float* img, const float* weight) {
     if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
     dev::set_device(cfg_.device);
     View& vw = views_[v];
+    wait_upload(vw);
     const size_t bytes = sizeof(float) * local_voxels();
     if (!vw.img_owned) vw.img_owned = (float*)dev::alloc(bytes);
     if (!vw.weight_owned) vw.weight_owned = (float*)dev::alloc(bytes);
     dev::h2d(vw.img_owned, img, bytes, stream_);
     if (weight) dev::h2d(vw.weight_owned, weight, bytes, stream_);       // weight == nullptr: generated on the device later
     else dev::zero(vw.weight_owned, bytes, stream_);
+    dev::sync(stream_);       // the synchronous variant: the caller's buffers (possibly page-locked) are free again when this returns
+    vw.pending = false;
     vw.img = vw.img_owned;
     vw.weight = vw.weight_owned;
 }
@@ -504,8 +507,14 @@ void Engine::set_view_host_async(int v, const float* img, const float* weight) {
 }
 void Engine::set_view_device(int v, const float* img, const float* weight) {
     if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
-    views_[v].img = img;
-    views_[v].weight = weight;
+    View& vw = views_[v];
+    vw.img = img;
+    if (weight) { vw.weight = weight; return; }
+    // weight == nullptr: the weight mask will be generated on the device (mvd_make_blending_weights + mvd_normalize_weights)
+    dev::set_device(cfg_.device);
+    if (!vw.weight_owned) vw.weight_owned = (float*)dev::alloc(sizeof(float) * local_voxels());
+    dev::zero(vw.weight_owned, sizeof(float) * local_voxels(), stream_);
+    vw.weight = vw.weight_owned;
 }
 void Engine::set_psf(int v, const float* psf, const int kd[3]) {
     if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
@@ -690,19 +699,82 @@ void Engine::ensure_stats_slot() {
 // PsiInit on the device (M/process/deconvolution/init/PsiInitBlurredFused.java:63-127, PsiInitAvgPrecise.java:52-112,
 // PsiInitAvgApprox.java:47-99)
 // ------------------------------------------------------------------------------------------------
+void Engine::all_reduce(double* values, int count, int op) {
+    if (!is_sharded() || count <= 0) return;
+    if (host_reduce_) {
+        if (host_reduce_(host_reduce_user_, values, count, op) != 0) throw Error("the host's reduce callback failed");
+    } else if (comm_) {
+        comm_->all_reduce(values, count, op);
+    } else {
+        throw Error("a sharded context needs an attached communicator (mvd_comm_attach) or a reduce callback (mvd_set_reduce_callback) for its "
+                    "global statistics");
+    }
+}
+
+// Gauss3.gauss(sigma, extendMirrorSingle(psi), psi) on a sharded context: the blur reads r = k/2 voxels beyond the own box, more than the
+// halo the iterations need, so the un-blurred fused estimate of the own box is copied into a temporary array with an r-wide halo, the halo
+// is filled from the neighbours (their own boxes hold their part of the same global estimate), and the blurred own box is copied back.
+void Engine::psi_blur_sharded(const std::vector<float>& k3, int k) {
+    const Geometry& g = cfg_.geom;
+    const int r = k / 2;
+    Geometry gt = g;
+    for (int d = 1; d < 3; ++d) {
+        if (!sharded(d)) continue;
+        if (g.own_hi[d] - g.own_lo[d] < r) throw Error("sharded FUSED_BLURRED: every box must be at least (int)(3*sigma+0.5) voxels thick");
+        const int lo = std::max(0, g.own_lo[d] - r), hi = std::min(g.gdim[d], g.own_hi[d] + r);
+        gt.goff[d] = lo; gt.vol[d] = hi - lo;
+    }
+    const size_t nt = (size_t)gt.vol[0] * gt.vol[1] * gt.vol[2];
+    float* tin = (float*)dev::alloc(sizeof(float) * nt);
+    float* tout = nullptr;
+    cpx* khat = nullptr;
+    try {
+        tout = (float*)dev::alloc(sizeof(float) * nt);
+        dev::zero(tin, sizeof(float) * nt, stream_);
+        const int rows = g.own_hi[1] - g.own_lo[1], planes = g.own_hi[2] - g.own_lo[2];
+        copy_region(stream_, psi_[cur_], g.vol[1], g.own_lo[1] - g.goff[1], g.own_lo[2] - g.goff[2],
+                    tin, gt.vol[1], g.own_lo[1] - gt.goff[1], g.own_lo[2] - gt.goff[2], g.vol[0], rows, planes);
+        HaloBox b;
+        b.base = tin; b.row_floats = gt.vol[0]; b.nrows = gt.vol[1]; b.nplanes = gt.vol[2];
+        b.y0 = g.own_lo[1] - gt.goff[1]; b.y1 = g.own_hi[1] - gt.goff[1];
+        b.z0 = g.own_lo[2] - gt.goff[2]; b.z1 = g.own_hi[2] - gt.goff[2];
+        b.hy_lo = b.hy_hi = sharded(1) ? r : 0;
+        b.hz_lo = b.hz_hi = sharded(2) ? r : 0;
+        do_exchange(2, b, true);
+        Reach r1[3], r2[3];
+        const int kd[3] = {k, k, k};
+        for (int d = 0; d < 3; ++d) { r1[d] = reach_of(k); r2[d] = Reach{0, 0}; }
+        Convolver cv(gt, r1, r2, 0, cfg_.max_len, stream_, tables_.get());
+        khat = cv.build_khat(k3.data(), kd);
+        cv.conv(tin, tout, khat, EXT_MIRROR, 0.f);
+        copy_region(stream_, tout, gt.vol[1], g.own_lo[1] - gt.goff[1], g.own_lo[2] - gt.goff[2],
+                    psi_[cur_], g.vol[1], g.own_lo[1] - g.goff[1], g.own_lo[2] - g.goff[2], g.vol[0], rows, planes);
+        dev::sync(stream_);
+    } catch (...) {
+        dev::free_(tin); dev::free_(tout); dev::free_(khat);
+        throw;
+    }
+    dev::free_(tin); dev::free_(tout); dev::free_(khat);
+    exchange_psi(psi_[cur_]);                 // the halo of the iterations' psi array
+}
+
 void Engine::psi_init(int type, double sigma, double* avg_out, float* max_out, bool set_img_to_avg) {
     dev::set_device(cfg_.device);
     const int V = cfg_.num_views;
     if (V > MVD_MAX_VIEWS) throw Error("too many views for the device PsiInit");
     const Geometry& g = cfg_.geom;
-    const bool sharded = g.own_lo[2] != 0 || g.own_hi[2] != g.gdim[2];
-    if (g.own_lo[1] != 0 || g.own_hi[1] != g.gdim[1]) throw Error("device PsiInit supports z-slab sharding only; initialise psi from the host on a y-sharded context");
-    const long long plane = (long long)g.vol[0] * g.vol[1], n = (long long)local_voxels();
-    const long long own0 = (long long)(g.own_lo[2] - g.goff[2]) * plane, own1 = (long long)(g.own_hi[2] - g.goff[2]) * plane;
+    const bool shard = is_sharded();
+    if (shard && !can_reduce())
+        throw Error("PsiInit on a sharded context needs global statistics: attach a communicator (mvd_comm_attach) or a reduce callback "
+                    "(mvd_set_reduce_callback) first");
+    if (shard && type == PSI_FUSED_BLURRED && !has_exchange())
+        throw Error("PsiInit FUSED_BLURRED on a sharded context needs an attached exchange (mvd_comm_attach / mvd_set_exchange_callback)");
+    const long long n = (long long)local_voxels();
+    const OwnBox ob{g.vol[0], g.vol[1], g.own_lo[1] - g.goff[1], g.own_hi[1] - g.goff[1], g.own_lo[2] - g.goff[2], g.own_hi[2] - g.goff[2]};
     ViewPtrs vp;
     for (int j = 0; j < V; ++j) {
         if (!views_[j].img) throw Error("view without image");
-        if (views_[j].pending) { dev::stream_wait(stream_, views_[j].ready); views_[j].pending = false; }
+        wait_upload(views_[j]);
         vp.img[j] = views_[j].img;
         vp.weight[j] = views_[j].weight;
     }
@@ -711,19 +783,28 @@ void Engine::psi_init(int type, double sigma, double* avg_out, float* max_out, b
     double acc[2] = {0, 0};
     float mx[MVD_MAX_VIEWS] = {0};
     double avg = 0, avg_reported = 0;
+    auto reduce_max = [&](float lowest) {      // per-view maxima over all boxes (MultiViewDeconvolution.java:115-135: max[] is global)
+        double m[MVD_MAX_VIEWS];
+        for (int j = 0; j < V; ++j) m[j] = (double)mx[j];
+        (void)lowest;
+        all_reduce(m, V, 1);
+        for (int j = 0; j < V; ++j) mx[j] = (float)m[j];
+    };
     if (type == PSI_FUSED_BLURRED || type == PSI_AVG) {
         if (type == PSI_FUSED_BLURRED)
             for (int j = 0; j < V; ++j) if (!views_[j].weight) throw Error("FUSED_BLURRED needs the view weights");
-        psi_fused_stats(stream_, vp, V, type == PSI_FUSED_BLURRED ? psi_[cur_] : nullptr, n, own0, own1, acc_dev_, max_dev_);
+        psi_fused_stats(stream_, vp, V, type == PSI_FUSED_BLURRED ? psi_[cur_] : nullptr, n, ob, acc_dev_, max_dev_);
         dev::d2h(acc, acc_dev_, sizeof(acc), stream_);
         dev::d2h(mx, max_dev_, sizeof(float) * V, stream_);
         dev::sync(stream_);
-        if (acc[1] == 0) throw Error("None of the views covers the deconvolved area, did you set the bounding box right?");   // PsiInitBlurredFused.java:95-99
+        all_reduce(acc, 2, 0);
+        reduce_max(0.f);
+        if (acc[1] == 0 && type == PSI_FUSED_BLURRED)        // PsiInitBlurredFused.java:95-99; PsiInitAvgPrecise has no such failure (:90-97: NaN -> 1)
+            throw Error("None of the views covers the deconvolved area, did you set the bounding box right?");
         avg = acc[0] / acc[1];
         if (avg != avg) avg = 1.0;
         avg_reported = avg;
         if (type == PSI_AVG) {
-            if (sharded) throw Error("PsiInit AVG on a sharded context needs the global average: initialise psi from the host");
             if (set_img_to_avg) fill_volume(stream_, psi_[cur_], n, (float)avg);
         } else {
             // Gauss3.gauss(sigma, extendMirrorSingle(psi), psi) -- separable Gaussian expressed as one 3-d kernel through the FFT passes
@@ -734,32 +815,37 @@ void Engine::psi_init(int type, double sigma, double* avg_out, float* max_out, b
                 for (int y = 0; y < k; ++y)
                     for (int x = 0; x < k; ++x)
                         k3[((size_t)z * k + y) * k + x] = (float)(half[std::abs(z - r)] * half[std::abs(y - r)] * half[std::abs(x - r)]);
-            Reach r1[3], r2[3];
-            const int kd[3] = {k, k, k};
-            for (int d = 0; d < 3; ++d) { r1[d] = reach_of(k); r2[d] = Reach{0, 0}; }
-            if (sharded && ((g.own_lo[2] != 0 && g.own_lo[2] - r < g.goff[2]) || (g.own_hi[2] != g.gdim[2] && g.own_hi[2] + r > g.goff[2] + g.vol[2])))
-                throw Error("sharded FUSED_BLURRED: the local arrays need at least (int)(3*sigma+0.5)+1 halo planes");
-            Convolver cv(g, r1, r2, 0, cfg_.max_len, stream_, tables_.get());
-            cpx* khat = cv.build_khat(k3.data(), kd);
-            dev::d2d(psi_[cur_ ^ 1], psi_[cur_], sizeof(float) * n, stream_);     // halo planes keep the un-blurred values until the exchange
-            cv.conv(psi_[cur_], psi_[cur_ ^ 1], khat, EXT_MIRROR, 0.f);
-            dev::sync(stream_);
-            dev::free_(khat);
-            cur_ ^= 1;
+            if (shard) {
+                psi_blur_sharded(k3, k);
+            } else {
+                Reach r1[3], r2[3];
+                const int kd[3] = {k, k, k};
+                for (int d = 0; d < 3; ++d) { r1[d] = reach_of(k); r2[d] = Reach{0, 0}; }
+                Convolver cv(g, r1, r2, 0, cfg_.max_len, stream_, tables_.get());
+                cpx* khat = cv.build_khat(k3.data(), kd);
+                cv.conv(psi_[cur_], psi_[cur_ ^ 1], khat, EXT_MIRROR, 0.f);
+                dev::sync(stream_);
+                dev::free_(khat);
+                cur_ ^= 1;
+            }
         }
     } else if (type == PSI_APPROX_AVG) {
-        if (sharded) throw Error("PsiInit APPROX_AVG is not available on a sharded context");
+        // PsiInitAvgApproxThread.java:58-85: min / max / mean of the central x-hyperslice (visited numDimensions times: same mean)
+        double sums[2 * MVD_MAX_VIEWS];
         for (int j = 0; j < V; ++j) {
             dev::zero(acc_dev_, sizeof(double) * 2, stream_);
             const float lowest = -3.0e38f;
             dev::h2d(max_dev_, &lowest, sizeof(float), stream_);
             dev::sync(stream_);
-            slice_stats(stream_, views_[j].img, g.vol[0], (long long)g.vol[1] * g.vol[2], acc_dev_, max_dev_);
+            slice_stats(stream_, views_[j].img, ob, (long long)g.vol[1] * g.vol[2], acc_dev_, max_dev_);
             dev::d2h(acc, acc_dev_, sizeof(acc), stream_);
             dev::d2h(&mx[j], max_dev_, sizeof(float), stream_);
             dev::sync(stream_);
-            avg += acc[0] / acc[1];                          // the slice is visited numDimensions times: same mean
+            sums[2 * j] = acc[0]; sums[2 * j + 1] = acc[1];
         }
+        all_reduce(sums, 2 * V, 0);
+        reduce_max(-3.0e38f);
+        for (int j = 0; j < V; ++j) avg += sums[2 * j] / sums[2 * j + 1];
         avg /= (double)V;
         if (avg != avg) avg = 1.0;
         avg_reported = -1.0;                                 // PsiInitAvgApprox.getAvg(): the field is shadowed by a local (:40,57,80)
@@ -778,6 +864,7 @@ void Engine::make_blending_weights(int v, const int box_min[3], const int box_ma
     if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
     dev::set_device(cfg_.device);
     View& vw = views_[v];
+    wait_upload(vw);          // an asynchronous upload of this view zeroes / fills weight_owned on the copy stream
     if (vw.weight && !vw.weight_owned) throw Error("the weight of this view is borrowed device memory; cannot generate into it");
     if (!vw.weight_owned) vw.weight_owned = (float*)dev::alloc(sizeof(float) * local_voxels());
     vw.weight = vw.weight_owned;
@@ -795,6 +882,7 @@ void Engine::fuse_group_host(int v, const RawViewDev* views_host, int count, con
     if (count < 1 || count > 64) throw Error("a group needs 1..64 views");
     dev::set_device(cfg_.device);
     View& vw = views_[v];
+    wait_upload(vw);
     if ((vw.img && !vw.img_owned) || (vw.weight && !vw.weight_owned)) throw Error("this view borrows device memory; cannot generate into it");
     const size_t bytes = sizeof(float) * local_voxels();
     if (!vw.img_owned) vw.img_owned = (float*)dev::alloc(bytes);
@@ -853,6 +941,7 @@ void Engine::normalize_view_weights(double osem_speedup, bool additional_smooth,
     WeightPtrs w;
     for (int j = 0; j < V; ++j) {
         if (!views_[j].weight_owned || views_[j].weight != views_[j].weight_owned) throw Error("normalisation needs context-owned weights for every view");
+        wait_upload(views_[j]);
         w.w[j] = views_[j].weight_owned;
     }
     normalize_weights(stream_, w, V, (long long)local_voxels(), osem_speedup, additional_smooth, max_diff_range, scaling_range);
@@ -862,13 +951,14 @@ void Engine::get_image_host(int v, float* out) {
     if (v < 0 || v >= cfg_.num_views || !views_[v].img) throw Error("no such image");
     dev::set_device(cfg_.device);
     View& vw = views_[v];
-    if (vw.pending) { dev::stream_wait(stream_, vw.ready); vw.pending = false; }
+    wait_upload(vw);
     dev::d2h(out, vw.img, sizeof(float) * local_voxels(), stream_);
     dev::sync(stream_);
 }
 void Engine::get_weight_host(int v, float* out) {
     if (v < 0 || v >= cfg_.num_views || !views_[v].weight) throw Error("no such weight");
     dev::set_device(cfg_.device);
+    wait_upload(views_[v]);
     dev::d2h(out, views_[v].weight, sizeof(float) * local_voxels(), stream_);
     dev::sync(stream_);
 }
@@ -895,7 +985,7 @@ void Engine::iteration_mul() {
     for (int v = 0; v < V; ++v) {                            // all views from the SAME psi
         View& vw = views_[v];
         if (!vw.img || !vw.weight) throw Error("view without image/weight");
-        if (vw.pending) { dev::stream_wait(stream_, vw.ready); vw.pending = false; }
+        wait_upload(vw);
         conv_->integral(psi_[cur_], vw.img, vw.k1hat, vw.k2hat, integral_[v]);
         mp.integral[v] = integral_[v];
         mp.weight[v] = vw.weight;
@@ -917,7 +1007,7 @@ void Engine::view_update(int v) {
     if (!vw.img || !vw.weight) throw Error("view without image/weight");
     if (cfg_.exchange_scheme == 1 && (sharded(1) || sharded(2)) && !has_exchange())
         throw Error("exchange scheme 1: attach a communicator (mvd_comm_attach) or an exchange callback before the first view update");
-    if (vw.pending) { dev::stream_wait(stream_, vw.ready); vw.pending = false; }
+    wait_upload(vw);
     ensure_stats_slot();
     const int nparts = conv_->num_tiles() * conv_->parts_per_tile();
     conv_->view_update(psi_[cur_], psi_[cur_ ^ 1], vw.img, vw.weight, vw.k1hat, vw.k2hat, cfg_.lambda, cfg_.min_value,
@@ -948,12 +1038,12 @@ void Engine::comm_attach(std::shared_ptr<NcclComm> comm, int py, int pz) {
     install_mid_exchange();
 }
 
-void Engine::do_exchange(int which, const HaloBox& b) {
+void Engine::do_exchange(int which, const HaloBox& b, bool oversize) {
     if (host_exchange_) {
         dev::sync(stream_);
         if (host_exchange_(host_exchange_user_, which, &b) != 0) throw Error("the host's exchange callback failed");
     } else if (comm_) {
-        comm_->exchange(b);
+        comm_->exchange(b, oversize);
     }
 }
 
@@ -1003,6 +1093,15 @@ void Engine::fetch_stats(int count, IterStats* out) {
     std::vector<double> h(2 * (size_t)std::max(count, 1));
     if (count > 0) dev::d2h(h.data(), stats_dev_ + 2 * (size_t)(stats_count_ - count), sizeof(double) * 2 * count, stream_);
     dev::sync(stream_);
+    if (is_sharded() && can_reduce() && count > 0) {
+        // IterationStatistics over the whole volume (MultiViewDeconvolutionSeq.java:165-176 sums the blocks' sumChange and takes the largest
+        // maxChange): collective -- every rank fetches the same number of entries
+        std::vector<double> sums((size_t)count), maxs((size_t)count);
+        for (int i = 0; i < count; ++i) { sums[i] = h[2 * i]; maxs[i] = h[2 * i + 1]; }
+        all_reduce(sums.data(), count, 0);
+        all_reduce(maxs.data(), count, 1);
+        for (int i = 0; i < count; ++i) { h[2 * i] = sums[i]; h[2 * i + 1] = maxs[i]; }
+    }
     for (int i = 0; i < count; ++i) { out[i].sum_change = h[2 * i]; out[i].max_change = h[2 * i + 1]; }
 }
 

@@ -156,13 +156,17 @@ struct HaloBox {
     int hy_lo, hy_hi, hz_lo, hz_hi;      // halo rows / planes wanted below (lo) and above (hi) the own region
 };
 typedef int (*ExchangeFn)(void* user, int which, const HaloBox* box);      // host-provided exchange (mvd_exchange_fn)
+typedef int (*ReduceFn)(void* user, double* values, int count, int op);    // host-provided all-reduce, in place (mvd_reduce_fn); op 0 sum, 1 max
 
 class HaloComm {
   public:
     // collective over the communicator.  need_y / need_z: floats this rank pushes per y / z neighbour and exchange at most.
     HaloComm(std::shared_ptr<NcclComm> comm, int py, int pz, stream_t s, size_t need_y, size_t need_z);
     ~HaloComm();
-    void exchange(const HaloBox& b);     // enqueued on the stream; the host does not block
+    // enqueued on the stream; the host does not block.  force_nccl: a one-off exchange larger than the landing buffers (PsiInit);
+    // every rank must pass the same value
+    void exchange(const HaloBox& b, bool force_nccl = false);
+    void all_reduce(double* host_values, int count, int op);      // collective, synchronises the stream; op 0 sum, 1 max
     int transport() const { return peer_ ? 1 : 0; }      // 0: NCCL send/recv, 1: direct stores into the neighbours' memory
   private:
     void reserve(size_t floats);
@@ -175,6 +179,8 @@ class HaloComm {
     stream_t stream_;
     size_t stage_floats_ = 0;
     float* stage_[4] = {nullptr, nullptr, nullptr, nullptr};
+    double* red_dev_ = nullptr;
+    size_t red_cap_ = 0;
     // peer transport: one region per rank = 8 landing buffers ({from lower y, from upper y, from lower z, from upper z} x parity)
     // + 4 arrival counters, mapped into the neighbours with CUDA IPC (or used directly when the neighbour lives in this process)
     bool peer_ = false;
@@ -192,9 +198,12 @@ class HaloComm {
 struct ViewPtrs { const float* img[MVD_MAX_VIEWS]; const float* weight[MVD_MAX_VIEWS]; };
 struct WeightPtrs { float* w[MVD_MAX_VIEWS]; };
 struct MulPtrs { const float* integral[MVD_MAX_VIEWS]; const float* weight[MVD_MAX_VIEWS]; };
-void psi_fused_stats(stream_t s, const ViewPtrs& vp, int V, float* psi, long long n, long long own0, long long own1, double* acc_dev, float* max_dev);
+// the own (responsibility) region of a local [.][ny][nx] array in array indices, half open
+struct OwnBox { int nx, ny; int y0, y1, z0, z1; };
+void psi_fused_stats(stream_t s, const ViewPtrs& vp, int V, float* psi, long long n, const OwnBox& ob, double* acc_dev, float* max_dev);
 void fill_volume(stream_t s, float* p, long long n, float v);
-void slice_stats(stream_t s, const float* img, int nx, long long nyz, double* acc_dev, float* max_dev);
+void slice_stats(stream_t s, const float* img, const OwnBox& ob, long long nyz, double* acc_dev, float* max_dev);
+void copy_region(stream_t s, const float* src, int sny, int sy0, int sz0, float* dst, int dny, int dy0, int dz0, int nx, int rows, int planes);
 void blend_weights(stream_t s, float* out, const double* lut_dev, const int vol[3], const int goff[3], const int box_min[3], const int box_max[3],
                    const float border[3], const float blending[3], const double* inv_affine = nullptr, const int* bbox_offset = nullptr);
 std::vector<double> blend_lut();
@@ -280,6 +289,12 @@ class Engine {
     void comm_attach(std::shared_ptr<NcclComm> comm, int py, int pz);
     // host-provided exchange instead of NCCL (the stream is synchronised before every call; see mvd_set_exchange_callback)
     void set_exchange_callback(ExchangeFn fn, void* user) { host_exchange_ = fn; host_exchange_user_ = user; install_mid_exchange(); }
+    // host-provided all-reduce for the global quantities of a sharded job (per-view maxima, PsiInit average, iteration statistics);
+    // with an attached communicator the library uses ncclAllReduce instead
+    void set_reduce_callback(ReduceFn fn, void* user) { host_reduce_ = fn; host_reduce_user_ = user; }
+    bool is_sharded() const { return sharded(1) || sharded(2); }
+    bool can_reduce() const { return host_reduce_ != nullptr || comm_ != nullptr; }
+    void all_reduce(double* values, int count, int op);      // no-op on an unsharded context
     void exchange_halos();
     int exchange_transport() const { return host_exchange_ ? 2 : (comm_ ? comm_->transport() : -1); }
     void view_update(int v);                               // asynchronous on the engine stream
@@ -310,6 +325,8 @@ class Engine {
         bool pending = false;
     };
     stream_t copy_stream_ = nullptr;
+    // every use of a view's image / weight on the compute stream first waits for its (asynchronous) upload
+    void wait_upload(View& vw) { if (vw.pending) { dev::stream_wait(stream_, vw.ready); vw.pending = false; } }
     std::unique_ptr<Convolver> small_conv_;   // cached plan of the PSF-derivation convolutions
     int small_dims_[3] = {0, 0, 0}, small_kd_[3] = {0, 0, 0};
     float* small_buf_ = nullptr; size_t small_buf_cap_ = 0;      // scratch of conv_same, reused across the derivation
@@ -335,10 +352,13 @@ class Engine {
     double last_fuse_ms_ = 0.0;
     ExchangeFn host_exchange_ = nullptr;
     void* host_exchange_user_ = nullptr;
+    ReduceFn host_reduce_ = nullptr;
+    void* host_reduce_user_ = nullptr;
+    void psi_blur_sharded(const std::vector<float>& k3, int k);
     Reach r1_[3] = {{0, 0}, {0, 0}, {0, 0}}, r2_[3] = {{0, 0}, {0, 0}, {0, 0}};     // kernel reaches (max over views)
     bool sharded(int d) const { return cfg_.geom.own_lo[d] != 0 || cfg_.geom.own_hi[d] != cfg_.geom.gdim[d]; }
     bool has_exchange() const { return comm_ != nullptr || host_exchange_ != nullptr; }
-    void do_exchange(int which, const HaloBox& b);
+    void do_exchange(int which, const HaloBox& b, bool oversize = false);
     void exchange_psi(float* psi);
     HaloBox psi_box(float* psi) const;
     HaloBox spectrum_box(cpx* work, const TileGeom& t) const;

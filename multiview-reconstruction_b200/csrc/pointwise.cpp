@@ -74,14 +74,20 @@ MVD_HD float fused_voxel(const ViewPtrs& vp, int V, long long i, double& mean_po
     return sumW > 0 ? (float)(sumI / sumW) : 0.f;
 }
 
+MVD_HD bool in_own_box(const OwnBox& b, long long i) {
+    const long long r = i / b.nx;
+    const int y = (int)(r % b.ny), z = (int)(r / b.ny);
+    return y >= b.y0 && y < b.y1 && z >= b.z0 && z < b.z1;
+}
+
 #ifndef MVD_HOST_EMU
-__global__ void psi_fused_kernel(ViewPtrs vp, int V, float* psi, long long n, long long own0, long long own1, double* acc, float* gmax) {
+__global__ void psi_fused_kernel(ViewPtrs vp, int V, float* psi, long long n, OwnBox ob, double* acc, float* gmax) {
     double s = 0, c = 0;
     float vmax[MVD_MAX_VIEWS];
     for (int j = 0; j < MVD_MAX_VIEWS; ++j) vmax[j] = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         double mp; bool cov;
-        const bool own = i >= own0 && i < own1;
+        const bool own = in_own_box(ob, i);
         const float v = fused_voxel(vp, V, i, mp, cov, own ? vmax : nullptr);
         if (psi) psi[i] = v;
         if (own && cov) { s += mp; c += 1.0; }
@@ -91,17 +97,17 @@ __global__ void psi_fused_kernel(ViewPtrs vp, int V, float* psi, long long n, lo
 }
 #endif
 
-void psi_fused_stats(stream_t s, const ViewPtrs& vp, int V, float* psi, long long n, long long own0, long long own1, double* acc_dev, float* max_dev) {
+void psi_fused_stats(stream_t s, const ViewPtrs& vp, int V, float* psi, long long n, const OwnBox& ob, double* acc_dev, float* max_dev) {
     dev::zero(acc_dev, sizeof(double) * 2, s);
     dev::zero(max_dev, sizeof(float) * MVD_MAX_VIEWS, s);
 #ifndef MVD_HOST_EMU
-    psi_fused_kernel<<<148 * 8, 256, 0, s>>>(vp, V, psi, n, own0, own1, acc_dev, max_dev);
+    psi_fused_kernel<<<148 * 8, 256, 0, s>>>(vp, V, psi, n, ob, acc_dev, max_dev);
     MVD_CUDA_CHECK(cudaGetLastError());
 #else
     double sum = 0, cnt = 0;
     for (long long i = 0; i < n; ++i) {
         double mp; bool cov;
-        const bool own = i >= own0 && i < own1;
+        const bool own = in_own_box(ob, i);
         const float v = fused_voxel(vp, V, i, mp, cov, own ? max_dev : nullptr);
         if (psi) psi[i] = v;
         if (own && cov) { sum += mp; cnt += 1.0; }
@@ -118,28 +124,46 @@ void fill_volume(stream_t s, float* p, long long n, float v) { pfor(n, FillValue
 
 // PsiInitAvgApproxThread (init/PsiInitAvgApproxThread.java:58-85): min / max / mean of the central x-hyperslice
 struct SliceStats {
-    const float* img; int nx, ny; long long nyz; double* acc; float* gmax;   // acc = {sum, count}
+    const float* img; OwnBox ob; long long nyz; double* acc; float* gmax;   // acc = {sum, count}
 };
 #ifndef MVD_HOST_EMU
 __global__ void slice_stats_kernel(SliceStats a) {
     double s = 0, c = 0; float m = -3.0e38f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.nyz; i += (long long)gridDim.x * blockDim.x) {
-        const float v = a.img[i * a.nx + a.nx / 2];
+        if (!in_own_box(a.ob, i * a.ob.nx)) continue;
+        const float v = a.img[i * a.ob.nx + a.ob.nx / 2];
         s += (double)v; c += 1.0; m = fmaxf(m, v);
     }
     block_accumulate(s, c, m, a.acc, a.acc + 1, a.gmax);
 }
 #endif
-void slice_stats(stream_t s, const float* img, int nx, long long nyz, double* acc_dev, float* max_dev) {
-    SliceStats a{img, nx, 0, nyz, acc_dev, max_dev};
+void slice_stats(stream_t s, const float* img, const OwnBox& ob, long long nyz, double* acc_dev, float* max_dev) {
+    SliceStats a{img, ob, nyz, acc_dev, max_dev};
 #ifndef MVD_HOST_EMU
     slice_stats_kernel<<<148, 256, 0, s>>>(a);
     MVD_CUDA_CHECK(cudaGetLastError());
 #else
-    double sum = 0; float m = -3.0e38f;
-    for (long long i = 0; i < nyz; ++i) { const float v = img[i * nx + nx / 2]; sum += v; m = std::max(m, v); }
-    acc_dev[0] += sum; acc_dev[1] += (double)nyz; *max_dev = std::max(*max_dev, m);
+    double sum = 0, cnt = 0; float m = -3.0e38f;
+    for (long long i = 0; i < nyz; ++i) {
+        if (!in_own_box(ob, i * ob.nx)) continue;
+        const float v = img[i * ob.nx + ob.nx / 2]; sum += v; cnt += 1.0; m = std::max(m, v);
+    }
+    acc_dev[0] += sum; acc_dev[1] += cnt; *max_dev = std::max(*max_dev, m);
 #endif
+}
+
+// copy rows x planes of nx floats between two [.][ny][nx] arrays of different extents (PsiInit on a sharded context)
+struct CopyRegion {
+    const float* src; float* dst; int nx, rows; int sny, sy0, sz0, dny, dy0, dz0;
+    MVD_HD void operator()(long long i) const {
+        const int x = (int)(i % nx);
+        const long long r = i / nx;
+        const int y = (int)(r % rows), z = (int)(r / rows);
+        dst[((long long)(dz0 + z) * dny + (dy0 + y)) * nx + x] = src[((long long)(sz0 + z) * sny + (sy0 + y)) * nx + x];
+    }
+};
+void copy_region(stream_t s, const float* src, int sny, int sy0, int sz0, float* dst, int dny, int dy0, int dz0, int nx, int rows, int planes) {
+    pfor((long long)nx * rows * planes, CopyRegion{src, dst, nx, rows, sny, sy0, sz0, dny, dy0, dz0}, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -205,3 +205,14 @@ def host_exchange_callback(ry, rz, py, pz, rank_of, dist, device=None):
         if device is not None:
             torch.cuda.synchronize(device)
     return cb
+
+
+def host_reduce_callback(dist):
+    """A reduce callback for DeconViews.set_reduce_callback built on torch.distributed (CPU tensors: works with gloo, and with
+    nccl groups that have a gloo side group)."""
+    import torch
+
+    def cb(values, op):
+        t = torch.from_numpy(values)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 1 else dist.ReduceOp.SUM)
+    return cb

@@ -119,3 +119,29 @@ def test_hostemu_reproduces_prep_golden(hostemu_lib, oracle, prep):
             assert np.array_equal(dv.getWeight(j), g[f"norm_smooth{j}"])
     finally:
         dv.close()
+
+
+# ---- BASELINE config c1 in full (tests/golden/c1_case.npz, made by tests/golden/make_golden_c1.py) ---------------------------------
+def test_oracle_float32_reproduces_c1_golden_first_iteration(oracle):
+    """the float32 oracle (the CPU baseline bench.py times) against the float64 golden of config c1: iteration 1 on the full
+    256 x 256 x 128 volume with the 25 x 19 x 25 PSFs; pins the seeded inputs, the kernels' (quirky) sums and the statistics"""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_c1", os.path.join(here, "golden", "make_golden_c1.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    g = np.load(os.path.join(here, "golden", "c1_case.npz"))
+    ds, views, psi0, avg = gen.inputs()
+    assert np.allclose([float(im.sum(dtype=np.float64)) for im in ds.images], g["img_sums"], rtol=1e-12)
+    assert np.allclose([float(w.sum(dtype=np.float64)) for w in ds.weights], g["weight_sums"], rtol=1e-12)
+    assert np.allclose([float(v.kernel1.sum(dtype=np.float64)) for v in views], g["k1_sums"], atol=1e-7)
+    assert np.allclose([float(v.kernel2.sum(dtype=np.float64)) for v in views], g["k2_sums"], atol=1e-6)
+    assert abs(g["k1_sums"][0] - 1.0) > 5e-3                        # the reference's kernels do not sum to 1 (AdjustInput.java:115-119): view 0 is off by 0.77 %
+    assert abs(avg - float(g["avg"])) <= 1e-9 * abs(avg) and np.array_equal(np.array([v.max_intensity for v in views], np.float32), g["max"])
+    psi = psi0
+    for v in range(4):
+        psi, s, m = oracle.view_update_whole(psi, views[v], 0.0, dtype=np.float32)
+        _, _, s_ref, m_ref = g["stats"][v]
+        assert abs(s - s_ref) <= 1e-4 * abs(s_ref) + 0.5 and abs(m - m_ref) <= 1e-3 * abs(m_ref) + 1e-3
+    step = int(g["lattice_step"])
+    assert oracle.rel_l2(psi[::step, ::step, ::step], g["psi_it1"]) <= REL_TOL(0)

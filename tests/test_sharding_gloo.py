@@ -238,3 +238,86 @@ def test_four_boxes_2d_grid(hostemu_lib, oracle, tmp_path, scheme):
         zlo, zhi = sharding.slab_range(nz, 2, rz)
         got[zlo:zhi, ylo:yhi] = np.load(tmp_path / f"box{r}.npy")
     assert oracle.rel_l2(got, ref) < 4e-6
+
+
+# ---- PsiInit, per-view maxima and IterationStatistics on a 2 x 2 (y x z) grid: global quantities through the reduce callback -------
+def _worker_psiinit(rank, world, port, lib_path, out_dir, kind):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch.distributed as dist
+    import mvdecon_oracle as o
+    import mvrecon_b200 as m
+    from mvrecon_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = m.Lib(lib_path)
+    ds = o.make_synthetic(DIMS_2D, VIEWS, seed=8, **KW_CB)
+    nz, ny, nx = DIMS_2D
+    py, pz = 2, 2
+    ry, rz = rank // pz, rank % pz
+    H = 2                                                       # exchange scheme 1: max(k1/2, k2/2)
+    ylo, yhi = sharding.slab_range(ny, py, ry)
+    zlo, zhi = sharding.slab_range(nz, pz, rz)
+    y0, y1 = sharding.extended_range(ylo, yhi, ny, H)
+    z0, z1 = sharding.extended_range(zlo, zhi, nz, H)
+    cut = lambda a: np.ascontiguousarray(a[z0:z1, y0:y1])
+    loc = [m.DeconView(cut(ds.images[v]), cut(ds.weights[v]), ds.psfs[v], m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(VIEWS)]
+    dv = m.DeconViews(loc, global_dims_zyx=DIMS_2D, library=lib, exchange_scheme=1,
+                      shard=(zlo, zhi, z0, z1 - z0), shard_y=(ylo, yhi, y0, y1 - y0))
+    init = {"fused": m.PsiInitBlurredFused(1.5), "avg": m.PsiInitAvgPrecise(), "approx": m.PsiInitAvgApprox()}[kind]
+    with pytest.raises(m.MvdError, match="sharded"):            # global statistics need the reduce plumbing first
+        init.runInitialization(dv)
+    dv.set_exchange_callback(sharding.host_exchange_callback(ry, rz, py, pz, lambda a, b: a * pz + b, dist))
+    dv.set_reduce_callback(sharding.host_reduce_callback(dist))
+    dec = m.MultiViewDeconvolutionSeq(dv, 1, init)
+    assert dec.initWasSuccessful()
+    np.save(os.path.join(out_dir, f"psi0_{rank}.npy"), dec.getPSI())           # the whole local array: halos must hold the neighbours' values
+    dec.runIterations()
+    np.save(os.path.join(out_dir, f"box{rank}.npy"), dec.getPSI()[zlo - z0:zhi - z0, ylo - y0:yhi - y0])
+    np.save(os.path.join(out_dir, f"meta{rank}.npy"), np.array([init.getAvg()] + list(init.getMax()) +
+                                                               [x for s in dec.stats[0] for x in (s.sumChange, s.maxChange)]))
+    dv.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["fused", "avg", "approx"])
+def test_psi_init_and_statistics_on_a_2d_grid(hostemu_lib, oracle, tmp_path, kind):
+    """PsiInitBlurredFused / AvgPrecise / AvgApprox on y x z sharded contexts (PsiInitBlurredFused.java:76-127, MultiViewDeconvolution.java:115-135):
+    psi0, avg and max[] equal the whole-volume values on every rank; the statistics of a view update are summed / maxed over the boxes
+    (MultiViewDeconvolutionSeq.java:165-176)."""
+    import torch.multiprocessing as mp
+    from mvrecon_b200 import sharding
+    world = 4
+    port = 35500 + (os.getpid() % 2000) + {"fused": 0, "avg": 17, "approx": 29}[kind]
+    mp.start_processes(_worker_psiinit, args=(world, port, hostemu_lib.path, str(tmp_path), kind), nprocs=world, join=True, start_method="spawn")
+    ds = oracle.make_synthetic(DIMS_2D, VIEWS, seed=8, **KW_CB)
+    if kind == "fused":
+        psi0, mx, avg = oracle.psi_init_blurred_fused(ds.images, ds.weights, 1.5)
+    elif kind == "avg":
+        psi0, mx, avg = oracle.psi_init_avg_precise(ds.images)
+    else:
+        psi0, mx, avg = oracle.psi_init_avg_approx(ds.images)
+    k1, k2 = oracle.derive_kernels(ds.psfs, oracle.EFFICIENT_BAYESIAN)
+    views = [oracle.OracleView(ds.images[v], ds.weights[v], k1[v], k2[v], float(mx[v])) for v in range(VIEWS)]
+    ref, st = oracle.run_iterations_seq(psi0, views, 1, 0.0, dtype=np.float64)
+    nz, ny, nx = DIMS_2D
+    got = np.empty_like(ref, dtype=np.float32)
+    for r in range(world):
+        ry, rz = r // 2, r % 2
+        ylo, yhi = sharding.slab_range(ny, 2, ry)
+        zlo, zhi = sharding.slab_range(nz, 2, rz)
+        y0, y1 = sharding.extended_range(ylo, yhi, ny, 2)
+        z0, z1 = sharding.extended_range(zlo, zhi, nz, 2)
+        loc0 = np.load(tmp_path / f"psi0_{r}.npy")
+        assert oracle.rel_l2(loc0, psi0[z0:z1, y0:y1]) < 1e-6, (r, kind)
+        got[zlo:zhi, ylo:yhi] = np.load(tmp_path / f"box{r}.npy")
+        meta = np.load(tmp_path / f"meta{r}.npy")
+        assert abs(meta[0] - avg) <= 1e-9 * abs(avg)
+        assert np.array_equal(meta[1:1 + VIEWS].astype(np.float32), mx)
+        for v in range(VIEWS):
+            s_ref, m_ref = st[v][2], st[v][3]
+            assert abs(meta[1 + VIEWS + 2 * v] - s_ref) <= 1e-4 * abs(s_ref) + 0.5
+            assert abs(meta[2 + VIEWS + 2 * v] - m_ref) <= 1e-3 * abs(m_ref) + 1e-3
+    assert oracle.rel_l2(got, ref) < 4e-6
