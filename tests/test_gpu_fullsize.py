@@ -51,10 +51,12 @@ def test_c1_full_ten_iterations_against_oracle_and_golden(product_lib, oracle):
             stats = dec.runNextIteration()
             for v in range(4):
                 psi64, s, mx = oracle.view_update_whole(psi64, views[v], 0.0, dtype=np.float64)
-                assert abs(stats[v].sumChange - s) <= 2e-4 * abs(s) + 1.0
+                # sumChange is a SIGNED sum over 8.4 M voxels (DeconvolutionMethods.java:308): its float32 noise floor scales with sum |psi|
+                noise = 2e-7 * float(np.abs(psi64).sum(dtype=np.float64))
+                assert abs(stats[v].sumChange - s) <= 2e-4 * abs(s) + noise
                 assert abs(stats[v].maxChange - mx) <= 2e-3 * abs(mx) + 1e-3
                 _, _, s_ref, m_ref = gold["stats"][k]
-                assert abs(stats[v].sumChange - s_ref) <= 5e-4 * abs(s_ref) + 5.0 and abs(stats[v].maxChange - m_ref) <= 2e-3 * abs(m_ref) + 1e-3
+                assert abs(stats[v].sumChange - s_ref) <= 5e-4 * abs(s_ref) + 2 * noise and abs(stats[v].maxChange - m_ref) <= 2e-3 * abs(m_ref) + 1e-3
                 k += 1
             psi = dec.getPSI()
             assert oracle.rel_l2(psi, psi64) <= rel_tol(it), it
