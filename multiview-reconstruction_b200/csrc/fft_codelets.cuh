@@ -151,69 +151,106 @@ template <bool INV> MVD_HD void bfly5(cpx& a, cpx& b, cpx& c, cpx& d, cpx& e) {
 constexpr int first_factor(int R) {
     return R % 4 == 0 ? 4 : R % 2 == 0 ? 2 : R % 3 == 0 ? 3 : R % 5 == 0 ? 5 : R;
 }
-// frequency index held at position p after the no-reorder forward DFT of length R
-constexpr int freq_of_pos(int R, int p) {
-    if (R == 1) return 0;
-    int r = first_factor(R), m = R / r;
-    return (p / m) + r * freq_of_pos(m, p % m);
-}
 constexpr bool radix_supported(int R) {
     while (R % 2 == 0) R /= 2;
     while (R % 3 == 0) R /= 3;
     while (R % 5 == 0) R /= 5;
     return R == 1;
 }
+// Coprime split R = r * m for the prime-factor (Good-Thomas) step: r = the whole power of the smallest prime of R, or 0 when R is a
+// prime power.  With n = (m n1 + r n2) mod R the length-R DFT is an r x m two-dimensional DFT WITHOUT twiddle factors between the
+// two steps; the output frequency k is given by k = k1 mod r, k = k2 mod m (Chinese remainder theorem).
+constexpr int pfa_factor(int R) {
+    int p = R % 2 == 0 ? 2 : R % 3 == 0 ? 3 : R % 5 == 0 ? 5 : R;
+    int r = 1;
+    while (R % p == 0) { r *= p; R /= p; }
+    return R == 1 ? 0 : r;
+}
+// frequency index held at position p after the no-reorder forward DFT of length R
+constexpr int freq_of_pos(int R, int p) {
+    if (R == 1) return 0;
+    const int rp = pfa_factor(R);
+    if (rp == 0) {                                   // prime power: decimation in frequency with twiddles
+        int r = first_factor(R), m = R / r;
+        return (p / m) + r * freq_of_pos(m, p % m);
+    }
+    const int r = rp, m = R / rp;
+    for (int t = 0; t < r; ++t)
+        for (int s = 0; s < m; ++s)
+            if ((m * t + r * s) % R == p) {
+                const int k1 = freq_of_pos(r, t), k2 = freq_of_pos(m, s);
+                for (int k = 0; k < R; ++k)
+                    if (k % r == k1 && k % m == k2) return k;
+            }
+    return -1;
+}
 
 // ---------------------------------------------------------------------------------------------
-// recursive in-register DFT on a[OFF + i*STR], i in [0,R)
-//   forward: DIF  = (I_r (x) F_m) . D . (B_r (x) I_m)      (output scrambled, see freq_of_pos)
-//   inverse: exact conjugate transpose of the forward (unnormalised)
+// recursive in-register DFT over the elements a[Map::at(i)], i in [0,R)
+//   prime powers (Cooley-Tukey, decimation in frequency):
+//     forward: (I_r (x) F_m) . D . (B_r (x) I_m)      (output scrambled, see freq_of_pos)
+//   coprime factors (prime-factor algorithm): F_r along n1 then F_m along n2 of n = (m n1 + r n2) mod R, no twiddles --
+//     radix 6, 10, 12, 15, 18, 20, 24, 30 save all their internal twiddle multiplications
+//   inverse: exact conjugate transpose of the forward flow graph (unnormalised)
 // ---------------------------------------------------------------------------------------------
-template <int R, int OFF, int STR, bool INV, int E>
-struct Dft {
+template <int OFF, int STR> struct MapLin { static constexpr int at(int i) { return OFF + i * STR; } };
+template <class M, int Q, int LEN> struct MapBlock { static constexpr int at(int i) { return M::at(Q * LEN + i); } };           // Cooley-Tukey sub-block
+template <class M, int R, int r, int m, int N2> struct MapPfa1 { static constexpr int at(int i) { return M::at((m * i + r * N2) % R); } };   // along n1
+template <class M, int R, int r, int m, int T> struct MapPfa2 { static constexpr int at(int i) { return M::at((m * T + r * i) % R); } };     // along n2
+
+template <int R, class Map, bool INV, int E>
+struct DftM {
     static MVD_HD void run(cpx (&a)[E]) {
         if constexpr (R > 1) {
             static_assert(radix_supported(R), "radix must be 2^a 3^b 5^c");
-            constexpr int r = first_factor(R);
-            constexpr int m = R / r;
-            if constexpr (!INV) {
-                static_for<0, m>([&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    bfly<r, j, m>(a);
-                    static_for<1, r>([&](auto qc) {
-                        constexpr int q = decltype(qc)::value;
-                        a[OFF + (j + q * m) * STR] = mul_tw<j * q, R, false>(a[OFF + (j + q * m) * STR]);
-                    });
-                });
-                static_for<0, r>([&](auto qc) {
-                    constexpr int q = decltype(qc)::value;
-                    Dft<m, OFF + q * m * STR, STR, false, E>::run(a);
-                });
+            constexpr int rp = pfa_factor(R);
+            if constexpr (rp != 0) {
+                constexpr int r = rp, m = R / rp;
+                if constexpr (!INV) {
+                    static_for<0, m>([&](auto c) { DftM<r, MapPfa1<Map, R, r, m, decltype(c)::value>, false, E>::run(a); });
+                    static_for<0, r>([&](auto c) { DftM<m, MapPfa2<Map, R, r, m, decltype(c)::value>, false, E>::run(a); });
+                } else {
+                    static_for<0, r>([&](auto c) { DftM<m, MapPfa2<Map, R, r, m, decltype(c)::value>, true, E>::run(a); });
+                    static_for<0, m>([&](auto c) { DftM<r, MapPfa1<Map, R, r, m, decltype(c)::value>, true, E>::run(a); });
+                }
             } else {
-                static_for<0, r>([&](auto qc) {
-                    constexpr int q = decltype(qc)::value;
-                    Dft<m, OFF + q * m * STR, STR, true, E>::run(a);
-                });
-                static_for<0, m>([&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    static_for<1, r>([&](auto qc) {
-                        constexpr int q = decltype(qc)::value;
-                        a[OFF + (j + q * m) * STR] = mul_tw<j * q, R, true>(a[OFF + (j + q * m) * STR]);
+                constexpr int r = first_factor(R);
+                constexpr int m = R / r;
+                if constexpr (!INV) {
+                    static_for<0, m>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        bfly<r, j, m>(a);
+                        static_for<1, r>([&](auto qc) {
+                            constexpr int q = decltype(qc)::value;
+                            a[Map::at(j + q * m)] = mul_tw<j * q, R, false>(a[Map::at(j + q * m)]);
+                        });
                     });
-                    bfly<r, j, m>(a);
-                });
+                    static_for<0, r>([&](auto qc) { DftM<m, MapBlock<Map, decltype(qc)::value, m>, false, E>::run(a); });
+                } else {
+                    static_for<0, r>([&](auto qc) { DftM<m, MapBlock<Map, decltype(qc)::value, m>, true, E>::run(a); });
+                    static_for<0, m>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        static_for<1, r>([&](auto qc) {
+                            constexpr int q = decltype(qc)::value;
+                            a[Map::at(j + q * m)] = mul_tw<j * q, R, true>(a[Map::at(j + q * m)]);
+                        });
+                        bfly<r, j, m>(a);
+                    });
+                }
             }
         }
     }
     template <int r, int j, int m>
     static MVD_HD void bfly(cpx (&a)[E]) {
-        constexpr int i0 = OFF + j * STR;
-        constexpr int d = m * STR;
-        if constexpr (r == 2) bfly2<INV>(a[i0], a[i0 + d]);
-        else if constexpr (r == 3) bfly3<INV>(a[i0], a[i0 + d], a[i0 + 2 * d]);
-        else if constexpr (r == 4) bfly4<INV>(a[i0], a[i0 + d], a[i0 + 2 * d], a[i0 + 3 * d]);
-        else bfly5<INV>(a[i0], a[i0 + d], a[i0 + 2 * d], a[i0 + 3 * d], a[i0 + 4 * d]);
+        if constexpr (r == 2) bfly2<INV>(a[Map::at(j)], a[Map::at(j + m)]);
+        else if constexpr (r == 3) bfly3<INV>(a[Map::at(j)], a[Map::at(j + m)], a[Map::at(j + 2 * m)]);
+        else if constexpr (r == 4) bfly4<INV>(a[Map::at(j)], a[Map::at(j + m)], a[Map::at(j + 2 * m)], a[Map::at(j + 3 * m)]);
+        else bfly5<INV>(a[Map::at(j)], a[Map::at(j + m)], a[Map::at(j + 2 * m)], a[Map::at(j + 3 * m)], a[Map::at(j + 4 * m)]);
     }
+};
+template <int R, int OFF, int STR, bool INV, int E>
+struct Dft {
+    static MVD_HD void run(cpx (&a)[E]) { DftM<R, MapLin<OFF, STR>, INV, E>::run(a); }
 };
 
 // R consecutive complex values <-> global memory; 16-byte vector accesses when R is even (callers guarantee 16-byte
