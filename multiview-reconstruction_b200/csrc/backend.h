@@ -119,6 +119,8 @@ struct LenOps {
     size_t smem_col, smem_x;
     int ntw_x;                                   // entries of the x-pass stage twiddle tables
     void (*fill_xtw)(cpx* out);                  // host: fills ntw_x entries
+    int ntw_col;                                 // entries of the column-pass stage twiddle tables
+    void (*fill_ctw)(cpx* out);                  // host: fills ntw_col entries
     void (*launch_col)(int mode, const ColArgs& a, int gx, int gy, stream_t s);
     void (*launch_x)(int kind, const XArgs& a, int nblocks, stream_t s);
 };

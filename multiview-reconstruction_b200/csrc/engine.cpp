@@ -28,16 +28,15 @@ const cpx* Tables::xtw(int M) {
     xtw_[M] = d;
     return d;
 }
-const cpx* Tables::tw(int N) {
+const cpx* Tables::tw(int N) {          // per-position stage twiddles of the column passes (LenOps::fill_ctw)
     auto it = tw_.find(N);
     if (it != tw_.end()) return it->second;
-    std::vector<cpx> h(N);
-    for (int k = 0; k < N; ++k) {
-        const double a = 2.0 * M_PI * (double)k / (double)N;
-        h[k] = cpx{(float)std::cos(a), (float)-std::sin(a)};
-    }
-    cpx* d = (cpx*)dev::alloc(sizeof(cpx) * N);
-    dev::h2d(d, h.data(), sizeof(cpx) * N, stream_);
+    const LenOps* o = find_len_ops(N);
+    if (!o) throw Error("no kernels for this length");
+    std::vector<cpx> h((size_t)o->ntw_col + 1);
+    o->fill_ctw(h.data());
+    cpx* d = (cpx*)dev::alloc(sizeof(cpx) * h.size());
+    dev::h2d(d, h.data(), sizeof(cpx) * h.size(), stream_);
     dev::sync(stream_);
     tw_[N] = d;
     return d;

@@ -44,7 +44,7 @@ class Tables {
   public:
     explicit Tables(stream_t s) : stream_(s) {}
     ~Tables();
-    const cpx* tw(int N);       // exp(-2 pi i k / N)
+    const cpx* tw(int N);       // per-position stage twiddles of the column passes (LenOps::fill_ctw)
     const cpx* twist(int M);    // exp(-i pi m / (2M))
     const cpx* xtw(int M);      // per-position stage twiddles of the x passes (LenOps::fill_xtw)
   private:

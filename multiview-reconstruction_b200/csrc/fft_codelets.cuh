@@ -24,10 +24,43 @@ namespace mvd {
 
 struct alignas(8) cpx { float x, y; };
 
+// Complex arithmetic.  On the device a complex number travels as ONE 64-bit register pair (re, im) through the packed f32x2
+// instructions of sm_100a (FADD2 / FMUL2 / FFMA2: two IEEE single-precision lanes per issue slot).  ptxas folds the half swaps,
+// per-half negations and scalar broadcasts written below as mov.b64 packing into operand modifiers (.LO_HI, .NP, .F32), so
+//   a + b, a - b, a -+ i b       : 1 instruction   (2 scalar)
+//   c * a, c * a + b  (c real)   : 1               (2)
+//   a * b, a * conj(b)           : 2               (4)
+// The host build (emulator, tests) uses the plain scalar formulas.
+#if defined(__CUDA_ARCH__)
+typedef unsigned long long pk64;
+MVD_HD pk64 pk2(float lo, float hi) { pk64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+MVD_HD pk64 pkc(cpx a) { return pk2(a.x, a.y); }
+MVD_HD cpx upk(pk64 v) { cpx r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+MVD_HD pk64 p_add(pk64 a, pk64 b) { pk64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+MVD_HD pk64 p_mul(pk64 a, pk64 b) { pk64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+MVD_HD pk64 p_fma(pk64 a, pk64 b, pk64 c) { pk64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+MVD_HD cpx operator+(cpx a, cpx b) { return upk(p_add(pkc(a), pkc(b))); }
+MVD_HD cpx operator-(cpx a, cpx b) { return upk(p_add(pkc(a), pk2(-b.x, -b.y))); }
+MVD_HD cpx c_add_mi(cpx a, cpx b) { return upk(p_add(pkc(a), pk2(b.y, -b.x))); }          // a - i b
+MVD_HD cpx c_add_pi(cpx a, cpx b) { return upk(p_add(pkc(a), pk2(-b.y, b.x))); }          // a + i b
+MVD_HD cpx c_scale(float c, cpx a) { return upk(p_mul(pkc(a), pk2(c, c))); }              // c a
+MVD_HD cpx c_fma(float c, cpx a, cpx b) { return upk(p_fma(pkc(a), pk2(c, c), pkc(b))); } // c a + b
+MVD_HD cpx c_fma_mi(float c, cpx a, cpx b) { return upk(p_fma(pk2(a.y, a.x), pk2(c, -c), pkc(b))); }   // b - i c a
+MVD_HD cpx c_fma_pi(float c, cpx a, cpx b) { return upk(p_fma(pk2(a.y, a.x), pk2(-c, c), pkc(b))); }   // b + i c a
+MVD_HD cpx cmul(cpx a, cpx b) { return upk(p_fma(pk2(a.y, a.x), pk2(-b.y, b.y), p_mul(pkc(a), pk2(b.x, b.x)))); }
+MVD_HD cpx cmul_conj(cpx a, cpx b) { return upk(p_fma(pk2(a.y, a.x), pk2(b.y, -b.y), p_mul(pkc(a), pk2(b.x, b.x)))); }  // a * conj(b)
+#else
 MVD_HD cpx operator+(cpx a, cpx b) { return cpx{a.x + b.x, a.y + b.y}; }
 MVD_HD cpx operator-(cpx a, cpx b) { return cpx{a.x - b.x, a.y - b.y}; }
+MVD_HD cpx c_add_mi(cpx a, cpx b) { return cpx{a.x + b.y, a.y - b.x}; }
+MVD_HD cpx c_add_pi(cpx a, cpx b) { return cpx{a.x - b.y, a.y + b.x}; }
+MVD_HD cpx c_scale(float c, cpx a) { return cpx{c * a.x, c * a.y}; }
+MVD_HD cpx c_fma(float c, cpx a, cpx b) { return cpx{c * a.x + b.x, c * a.y + b.y}; }
+MVD_HD cpx c_fma_mi(float c, cpx a, cpx b) { return cpx{b.x + c * a.y, b.y - c * a.x}; }
+MVD_HD cpx c_fma_pi(float c, cpx a, cpx b) { return cpx{b.x - c * a.y, b.y + c * a.x}; }
 MVD_HD cpx cmul(cpx a, cpx b) { return cpx{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 MVD_HD cpx cmul_conj(cpx a, cpx b) { return cpx{a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }  // a * conj(b)
+#endif
 
 // L2 prefetch of the 128-byte line containing p (no-op on the host)
 #if defined(__CUDA_ARCH__)
@@ -91,16 +124,15 @@ MVD_HD cpx mul_tw(cpx a) {
         constexpr float h = 0.70710678118654752440f;
         constexpr int o = (8 * k) / N;          // 1,3,5,7
         // forward twiddle = cos - i sin
-        constexpr float cs = (o == 1 || o == 7) ? 1.f : -1.f;
-        constexpr float sn0 = (o == 1 || o == 3) ? -1.f : 1.f;   // sign of imaginary part (forward)
+        constexpr float cs = (o == 1 || o == 7) ? h : -h;
+        constexpr float sn0 = (o == 1 || o == 3) ? -h : h;       // imaginary part (forward)
         constexpr float sn = INV ? -sn0 : sn0;
-        // (x + i y)(cs + i sn) h = h (cs x - sn y) + i h (sn x + cs y)
-        return cpx{h * (cs * a.x - sn * a.y), h * (sn * a.x + cs * a.y)};
+        return c_fma_pi(sn, a, c_scale(cs, a));                  // (cs + i sn) a
     } else {
         constexpr cx_pair t = cx_cossin_turn(k, N);
         constexpr float c = float(t.c);
         constexpr float s = float(INV ? t.s : -t.s);
-        return cpx{a.x * c - a.y * s, a.x * s + a.y * c};
+        return c_fma_pi(s, a, c_scale(c, a));                    // (c + i s) a
     }
 }
 
@@ -120,32 +152,32 @@ template <bool INV> MVD_HD void bfly2(cpx& a, cpx& b) {
 }
 template <bool INV> MVD_HD void bfly3(cpx& a, cpx& b, cpx& c) {
     constexpr float s = 0.86602540378443864676f;
-    cpx t = b + c;
-    cpx d = b - c;
-    cpx u{a.x - 0.5f * t.x, a.y - 0.5f * t.y};
+    const cpx t = b + c;
+    const cpx d = b - c;
+    const cpx u = c_fma(-0.5f, t, a);
     a = a + t;
-    // forward: X1 = u + s*(d.y, -d.x) ; X2 = u - s*(d.y, -d.x)
-    cpx r = INV ? cpx{-s * d.y, s * d.x} : cpx{s * d.y, -s * d.x};
-    b = u + r; c = u - r;
+    // forward: X1 = u - i s d ; X2 = u + i s d
+    if constexpr (!INV) { b = c_fma_mi(s, d, u); c = c_fma_pi(s, d, u); }
+    else { b = c_fma_pi(s, d, u); c = c_fma_mi(s, d, u); }
 }
 template <bool INV> MVD_HD void bfly4(cpx& a, cpx& b, cpx& c, cpx& d) {
-    cpx t0 = a + c, t1 = a - c, t2 = b + d, t3 = b - d;
-    cpx r = INV ? cpx{-t3.y, t3.x} : cpx{t3.y, -t3.x};   // -+ i * t3
-    a = t0 + t2; c = t0 - t2; b = t1 + r; d = t1 - r;
+    const cpx t0 = a + c, t1 = a - c, t2 = b + d, t3 = b - d;
+    a = t0 + t2; c = t0 - t2;
+    if constexpr (!INV) { b = c_add_mi(t1, t3); d = c_add_pi(t1, t3); }     // forward: t1 -+ i t3
+    else { b = c_add_pi(t1, t3); d = c_add_mi(t1, t3); }
 }
 template <bool INV> MVD_HD void bfly5(cpx& a, cpx& b, cpx& c, cpx& d, cpx& e) {
     constexpr float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
     constexpr float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
-    cpx t1 = b + e, t2 = c + d, t3 = b - e, t4 = c - d;
-    cpx m1{a.x + c1 * t1.x + c2 * t2.x, a.y + c1 * t1.y + c2 * t2.y};
-    cpx m2{a.x + c2 * t1.x + c1 * t2.x, a.y + c2 * t1.y + c1 * t2.y};
-    cpx n1{s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y};
-    cpx n2{s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y};
-    a = cpx{a.x + t1.x + t2.x, a.y + t1.y + t2.y};
+    const cpx t1 = b + e, t2 = c + d, t3 = b - e, t4 = c - d;
+    const cpx m1 = c_fma(c2, t2, c_fma(c1, t1, a));
+    const cpx m2 = c_fma(c1, t2, c_fma(c2, t1, a));
+    const cpx n1 = c_fma(s2, t4, c_scale(s1, t3));
+    const cpx n2 = c_fma(-s1, t4, c_scale(s2, t3));
+    a = a + t1 + t2;
     // forward: X1 = m1 - i n1, X4 = m1 + i n1, X2 = m2 - i n2, X3 = m2 + i n2
-    cpx r1 = INV ? cpx{-n1.y, n1.x} : cpx{n1.y, -n1.x};
-    cpx r2 = INV ? cpx{-n2.y, n2.x} : cpx{n2.y, -n2.x};
-    b = m1 + r1; e = m1 - r1; c = m2 + r2; d = m2 - r2;
+    if constexpr (!INV) { b = c_add_mi(m1, n1); e = c_add_pi(m1, n1); c = c_add_mi(m2, n2); d = c_add_pi(m2, n2); }
+    else { b = c_add_pi(m1, n1); e = c_add_mi(m1, n1); c = c_add_pi(m2, n2); d = c_add_mi(m2, n2); }
 }
 
 constexpr int first_factor(int R) {
@@ -310,18 +342,20 @@ MVD_HD void apply_tw(cpx (&a)[R], TwP&& twp) {
 }
 
 // One radix-R butterfly of one stage.  The line is accessed through functors:
-//   src(n) -> cpx, dst(n, cpx);  twf(k) -> exp(-2 pi i k / N), k in [0,N)   (global or shared-memory table).
+//   src(base, off) -> cpx, dst(base, off, cpx) for sample base + off (off a compile-time constant);
+//   tw(pc, j) -> the stage twiddle of butterfly position p at index j, exp(-2 pi i (N/BLK) freq_of_pos(R,p) j / N), from a
+//   per-position table [p-1][j] (global or shared memory): one base address per butterfly, compile-time offsets per position.
 // BLK = block length handled by this stage (N for the first stage), S = BLK/R the element stride.
 // Position p of the butterfly (element base + p*S) holds frequency freq_of_pos(R,p) of the radix-R DFT.
 template <int N, int BLK, int R, bool INV, class TwF, class Src, class Dst>
-MVD_HD void stage_bfly(int g, TwF&& twf, Src&& src, Dst&& dst) {
+MVD_HD void stage_bfly(int g, TwF&& tw, Src&& src, Dst&& dst) {
     constexpr int S = BLK / R;
     const int b = g / S;
     const int j = g - b * S;
     const int base = b * BLK + j;
     cpx a[R];
-    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; a[p] = src(base + p * S); });
-    auto twp = [&](auto pc) { constexpr int f = freq_of_pos(R, decltype(pc)::value); return twf((N / BLK) * f * j); };
+    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; a[p] = src(base, p * S); });
+    auto twp = [&](auto pc) { return tw(pc, j); };
     if constexpr (!INV) {
         Dft<R, 0, 1, false, R>::run(a);
         if constexpr (S > 1) apply_tw<R, false>(a, twp);
@@ -329,7 +363,7 @@ MVD_HD void stage_bfly(int g, TwF&& twf, Src&& src, Dst&& dst) {
         if constexpr (S > 1) apply_tw<R, true>(a, twp);
         Dft<R, 0, 1, true, R>::run(a);
     }
-    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; dst(base + p * S, a[p]); });
+    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; dst(base, p * S, a[p]); });
 }
 
 // last forward stage (S == 1) fused with the spectrum multiply and the first inverse stage:
@@ -340,12 +374,12 @@ MVD_HD void stage_conv(int g, Src&& src, Dst&& dst, Khat&& khat) {
     const int base = g * BLK;
     cpx a[R], kh[R];
     // the kernel-spectrum loads go out first: their (L2 / DRAM) latency overlaps the shared-memory reads and the forward DFT
-    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; kh[p] = khat(base + p); });
-    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; a[p] = src(base + p); });
+    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; kh[p] = khat(base, p); });
+    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; a[p] = src(base, p); });
     Dft<R, 0, 1, false, R>::run(a);
     static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; a[p] = cmul(a[p], kh[p]); });
     Dft<R, 0, 1, true, R>::run(a);
-    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; dst(base + p, a[p]); });
+    static_for<0, R>([&](auto pc) { constexpr int p = decltype(pc)::value; dst(base, p, a[p]); });
 }
 
 // frequency index (natural DFT order) stored at line position n after the full forward plan.

@@ -121,7 +121,7 @@ struct LenImpl {
     }
     static const LenOps* ops() {
         static const LenOps o = {P::N, P::R1, P::R2, P::R3, P::T, P::W, PX::XT, PX::XL, P::THREADS, PX::XTHREADS, smem_col, smem_x,
-                                 XLay<PX>::NTW, &fill_xtw<PX>, &launch_col, &launch_x};
+                                 XLay<PX>::NTW, &fill_xtw<PX>, StageTw<P>::NTW, &fill_stage_tw<P>, &launch_col, &launch_x};
         return &o;
     }
 };

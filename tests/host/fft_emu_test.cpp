@@ -32,13 +32,13 @@ static int test_plan() {
     std::uniform_real_distribution<float> U(-1.f, 1.f);
     for (auto& c : data) c = cpx{U(rng), U(rng)};
     orig = data;
-    std::vector<cpx> tw(N);
-    for (int k = 0; k < N; ++k) tw[k] = cpx{(float)std::cos(2 * M_PI * k / N), (float)-std::sin(2 * M_PI * k / N)};
+    std::vector<cpx> tw(StageTw<P>::NTW + 1);
+    fill_stage_tw<P>(tw.data());
     std::vector<cpx> khat(data.size());
     for (auto& c : khat) c = cpx{U(rng), U(rng)};
 
     ColArgs a{data.data(), khat.data(), tw.data(), stride_n, stride_b, nx, 0, 0, 0};
-    std::vector<cpx> sm(N * W + N);
+    std::vector<cpx> sm(ColSmem<P>::bytes() / sizeof(cpx) + 1);
     HostExec ex(P::THREADS);
     const int gx = (nx + W - 1) / W;
     auto run = [&](auto modec) {
