@@ -26,8 +26,12 @@ PLANS = [
 ]
 
 
-# hand-picked x plans (measured on B200); everything else is chosen by x_plan()
-XPLAN_OVERRIDE = {540: (15, 6, 6)}      # radix 27 needs ~120 registers (15 warps/SM): 3-stage measured 7 % faster on c3
+# hand-picked x plans "r1,r2,r3[,xt]" (measured on B200); everything else is chosen by x_plan()
+XPLAN_OVERRIDE = {
+    540: (18, 30, 1, 32),                       # measured against (15,6,6) and (20,27)
+    # three-stage lengths: last-stage radix 6 or 10 (no padding inside a line -> bulk-copy staging, conflict-free as is)
+    576: (12, 8, 6), 640: (8, 8, 10), 768: (16, 8, 6), 800: (10, 8, 10), 960: (12, 8, 10), 1152: (12, 16, 6),
+}
 
 
 def radix_ok(r):
@@ -38,47 +42,49 @@ def radix_ok(r):
 
 
 def x_plan(n, r1, r2, r3):
-    """Plan of the x kernels: two shared-memory stages whenever N = a*b with both radices <= 27 (halves the shared-memory traffic
-    and the barriers of the fused x passes); the last-stage radix is the even factor when exactly one is even (16-byte vector access),
-    else the smaller one.  XT = N / XR1 threads per line (one stage-1 butterfly each), XL lines per CTA (~200-288 threads,
-    padded lines below ~44 KB of shared memory)."""
-    best = None
+    """Plan of the x kernels.  Two shared-memory stages whenever N = a*b with a <= 20 (the stage whose butterfly stays in registers
+    across the real-space work) and b <= 30: half the shared-memory traffic and barriers of a three-stage plan (measured on c3:
+    quotient pass -9 %).  The last-stage radix b avoids multiples of 4 when it can (no padding inside a line: the lines are staged
+    by bulk copies in the persistent kernels, and odd or 2-mod-4 radices are bank-conflict free as they are); among those the
+    most balanced pair wins.  XT threads per line: N / r1 butterflies, rounded up to a whole warp when that wastes <= 10 % of the
+    lanes (a line never straddles a warp then).  XL lines per CTA: ~256 threads, line tile <= 36 KB (two tiles + tables per
+    persistent CTA, two CTAs per SM)."""
     forced = os.environ.get(f"MVD_XPLAN_{n}") or XPLAN_OVERRIDE.get(n)          # "r1,r2,r3[,xt]"
-    for a in range(2, 28):
-        if forced:
-            break
-        if n % a or not radix_ok(a):
-            continue
-        b = n // a
-        if b > 27 or b < 2 or not radix_ok(b):
-            continue
-        if best is None or max(a, b) < max(best):
-            best = (a, b)
     xt_forced = None
     if forced:
         f = [int(x) for x in (forced.split(",") if isinstance(forced, str) else forced)]
         xr1, xr2, xr3 = f[0], f[1], f[2]
         assert xr1 * xr2 * xr3 == n
         xt_forced = f[3] if len(f) > 3 else None
-    elif best:
-        a, b = best
-        if (a % 2 == 0) != (b % 2 == 0):
-            xr1, xr2 = (a, b) if b % 2 == 0 else (b, a)        # last stage even
-        else:
-            xr1, xr2 = max(a, b), min(a, b)
-        xr3 = 1
     else:
-        xr1, xr2, xr3 = r1, r2, r3
+        cands = []
+        for a in range(2, 21):
+            if n % a or not radix_ok(a):
+                continue
+            b = n // a
+            if b < 4 or a < 4 or b > 30 or not radix_ok(b):
+                continue
+            pad = 1 if b % 4 == 0 else 0
+            vec = 0 if b % 2 == 0 else 1
+            cands.append((pad, max(a, b), vec, a, b))
+        if cands:
+            _, _, _, xr1, xr2 = min(cands)
+            xr3 = 1
+        else:
+            xr1, xr2, xr3 = r1, r2, r3
     rl = xr3 if xr3 > 1 else xr2
     pad = 2 if rl % 4 == 0 else 0
     ls = n + pad * (n // rl)
-    xt = xt_forced or n // xr1
-    want = 224 if max(xr1, xr2) > 20 else 288
+    xt = n // xr1
+    if xt % 32 and (-xt) % 32 <= 0.10 * xt:
+        xt += (-xt) % 32
+    xt = xt_forced or xt
+    want = 256
     choice = None
     for xl in range(1, 129):
         thr = xt * xl
         smem = xl * ls * 8
-        if thr > 512 or smem > 44 * 1024:
+        if thr > 512 or smem > 36 * 1024:
             break
         score = abs(thr - want) + (0 if thr % 32 == 0 else 40)
         if choice is None or score < choice[0]:
