@@ -137,8 +137,8 @@ MVD_API int mvd_set_max_intensities(mvd_context* ctx, const float* max_per_view)
  * are mvd_set_psi + mvd_set_max_intensities).  Sets psi and the per-view maxima from the views already handed over
  * (PsiInitBlurredFused.java:63-127, PsiInitAvgPrecise.java:52-112, PsiInitAvgApprox.java:47-99).  sigma: Gaussian of FUSED_BLURRED
  * (reference default 5.0).  avg_out: PsiInit.getAvg() (APPROX_AVG reports -1 like the reference); max_out: num_views values.
- * Fails like the reference when no view covers the volume.  On a sharded context only FUSED_BLURRED is available (psi halos must be
- * exchanged afterwards; the maxima are per shard and must be all-reduced by the host).                                               */
+ * Fails like the reference when no view covers the volume (FUSED_BLURRED).  On a sharded context the call is collective: avg and the maxima
+ * are all-reduced over the attached communicator / reduce callback and the psi halos are exchanged.                                   */
 enum { MVD_PSI_FUSED_BLURRED = 0, MVD_PSI_AVG = 1, MVD_PSI_APPROX_AVG = 2 };
 MVD_API int mvd_psi_init(mvd_context* ctx, int type, double sigma, double* avg_out, float* max_out);
 /* PsiInitFromFile (M/process/deconvolution/init/PsiInitFromFile.java:44-93): psi := the TIFF stack at `path` opened as 32 bit (dimensions
@@ -207,6 +207,12 @@ MVD_API int mvd_run_iteration_mul(mvd_context* ctx, double stats[2]);
 /* One view update of MultiViewDeconvolutionSeq.runNextIteration (:69-176): psi <- update(psi, view v).
  * stats (may be NULL) receives {sumChange, maxChange} over the owned voxels (IterationStatistics, ComputeBlockThread.java:64-68). */
 MVD_API int mvd_run_view_update(mvd_context* ctx, int v, double stats[2]);
+/* DeconView.filterBlocksForContent (M/process/deconvolution/DeconView.java:204-274): on != 0 -> a (view, tile) pair whose weight volume
+ * is zero everywhere inside the tile is not computed any more (psi keeps its values there, the pair reports sumChange 0 / maxChange -1
+ * like a removed block).  The weights are examined now (the call synchronises) and again after every later change of a weight volume;
+ * skipped_out (may be NULL) receives the number of pairs currently dropped.  On a sharded context with exchange scheme 1 the call is
+ * collective and a tile is dropped only when it is empty on every rank (the neighbours read its quotient).  Off by default.            */
+MVD_API int mvd_skip_empty_tiles(mvd_context* ctx, int on, int* skipped_out);
 /* MultiViewDeconvolution.runIterations for n iterations; stats (may be NULL) receives n*num_views pairs.                */
 MVD_API int mvd_run_iterations(mvd_context* ctx, int n, double* stats);
 /* Asynchronous variant + explicit synchronisation (lets a multi-GPU host overlap its halo exchange).                    */

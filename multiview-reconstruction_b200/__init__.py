@@ -113,6 +113,7 @@ SYMBOLS = {
     "mvd_get_image": (C.c_int, [C.c_void_p, C.c_int, _F]),
     "mvd_run_iteration_mul": (C.c_int, [C.c_void_p, _D]),
     "mvd_run_view_update": (C.c_int, [C.c_void_p, C.c_int, _D]),
+    "mvd_skip_empty_tiles": (C.c_int, [C.c_void_p, C.c_int, _I]),
     "mvd_run_iterations": (C.c_int, [C.c_void_p, C.c_int, _D]),
     "mvd_enqueue_view_update": (C.c_int, [C.c_void_p, C.c_int]),
     "mvd_synchronize": (C.c_int, [C.c_void_p]),
@@ -564,6 +565,13 @@ class DeconViews:
         self.lib.check(self.lib.dll.mvd_normalize_weights(self._ctx, float(osemspeedup), 1 if additionalSmoothBlending else 0,
                                                            C.c_float(maxDiffRange), C.c_float(scalingRange)))
 
+    def filterBlocksForContent(self, on: bool = True) -> int:
+        """DeconView.filterBlocksForContent (DeconView.java:204-230) for the resident path: (view, tile) pairs without any weight are
+        not computed any more; returns how many pairs that is right now."""
+        n = C.c_int(0)
+        self.lib.check(self.lib.dll.mvd_skip_empty_tiles(self._ctx, 1 if on else 0, C.byref(n)))
+        return n.value
+
     def getWeight(self, v: int) -> np.ndarray:
         w = np.empty(self.local_shape, dtype=np.float32)
         self.lib.check(self.lib.dll.mvd_get_weight(self._ctx, int(v), _fp(w)))
@@ -921,10 +929,33 @@ def sortBlocksBySmallestFootprint(blocks: List[Block], psiDims_xyz, minRequiredB
     return layers if total == len(blocks) else [list(blocks)]
 
 
+def blockContainsContent(block: Block, weight: np.ndarray) -> bool:
+    """DeconView.blockContainsContent (DeconView.java:232-274): any weight != 0 inside the (zero-extended) block interval."""
+    return bool(np.any(block.copyBlock(weight, "zero") != 0.0))
+
+
+def filterBlocksForContent(blocksList: List[List[Block]], weight: np.ndarray) -> Tuple[int, int]:
+    """DeconView.filterBlocksForContent (DeconView.java:204-230): drops blocks without content and batches that became empty, in place;
+    returns (removed blocks, removed batches)."""
+    removeBlocks = removeBlockBatch = 0
+    for j in range(len(blocksList) - 1, -1, -1):
+        blocks = blocksList[j]
+        for i in range(len(blocks) - 1, -1, -1):
+            if not blockContainsContent(blocks[i], weight):
+                del blocks[i]
+                removeBlocks += 1
+        if not blocks:
+            del blocksList[j]
+            removeBlockBatch += 1
+    return removeBlocks, removeBlockBatch
+
+
 def runNextIterationBlocked(psi: np.ndarray, views: Sequence[DeconView], kernels: Sequence[Tuple[np.ndarray, np.ndarray]],
-                            max_intensities: Sequence[float], factory: ComputeBlockSeqThreadB200Factory) -> List[IterationStatistics]:
+                            max_intensities: Sequence[float], factory: ComputeBlockSeqThreadB200Factory,
+                            filterBlocks: bool = True) -> List[IterationStatistics]:
     """MultiViewDeconvolutionSeq.runNextIteration driven through the L2 operator, block by block with the reference's
-    delayed write-back (MultiViewDeconvolutionSeq.java:69-176).  psi is updated in place."""
+    delayed write-back (MultiViewDeconvolutionSeq.java:69-176); blocks without content are dropped like the DeconView constructor
+    does when asked to (DeconView.java:176-182; the GUI's testEmptyBlocks).  psi is updated in place."""
     worker = factory.create(0)
     out = []
     for v, view in enumerate(views):
@@ -934,7 +965,9 @@ def runNextIterationBlocked(psi: np.ndarray, views: Sequence[DeconView], kernels
         if blocks is None:
             raise MvdError("block smaller than the kernel")
         batches = sortBlocksBySmallestFootprint(blocks, psi.shape[::-1])
-        total = len(blocks)
+        if filterBlocks:
+            filterBlocksForContent(batches, view.weight)
+        total = len(blocks)                                             # DeconView.numBlocks: counted before the filter (DeconView.java:170)
         st = IterationStatistics()
         prev = []
         for batch in batches:

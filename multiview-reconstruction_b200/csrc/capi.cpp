@@ -191,6 +191,13 @@ int mvd_run_view_update(mvd_context* ctx, int v, double stats[2]) {
         if (stats) { stats[0] = s.sum_change; stats[1] = s.max_change; }
     });
 }
+int mvd_skip_empty_tiles(mvd_context* ctx, int on, int* skipped_out) {
+    return guarded([&] {
+        require(ctx, "null context");
+        const int n = ctx->engine->skip_empty_tiles(on != 0);
+        if (skipped_out) *skipped_out = n;
+    });
+}
 int mvd_run_iterations(mvd_context* ctx, int n, double* stats) {
     return guarded([&] {
         require(ctx && n >= 0, "bad argument");

@@ -320,11 +320,20 @@ void Convolver::conv(const float* src, float* dst, const cpx* khat, int ext, flo
 }
 
 void Convolver::view_update(const float* psi_in, float* psi_out, const float* img, const float* weight, const cpx* k1hat,
-                            const cpx* k2hat, float lambda, float min_value, float max_intensity, double* part_sum, float* part_max) {
+                            const cpx* k2hat, float lambda, float min_value, float max_intensity, double* part_sum, float* part_max,
+                            const unsigned char* skip) {
     if (xmode_ != 0) throw Error("internal: view updates need the real-packed x mode");
     int ti = 0;
     const int cp = chunk_planes_ > 0 ? chunk_planes_ : T_[2];
     for (const TileGeom& t : tiles_) {
+        if (skip && skip[ti]) {
+            // no content: psi keeps its values inside the tile's responsibility box (full x rows: tiles that split x are copied more than once)
+            copy_region(stream_, psi_in, g_.vol[1], t.lo[1] - g_.goff[1], t.lo[2] - g_.goff[2], psi_out, g_.vol[1], t.lo[1] - g_.goff[1],
+                        t.lo[2] - g_.goff[2], g_.vol[0], t.hi[1] - t.lo[1], t.hi[2] - t.lo[2]);
+            clear_parts(stream_, part_sum + (size_t)ti * xblocks_, part_max + (size_t)ti * xblocks_, xblocks_);
+            ++ti;
+            continue;
+        }
         XArgs a = base_xargs(t);
         // x/y pass chains run plane chunk by plane chunk so that the hand-over P1->P2, P4->P5->P6, P8->P9 stays in the 126 MB L2;
         // the z passes (P3, P7) need every plane and run over the whole tile.
@@ -464,7 +473,7 @@ Engine::~Engine() {
     dev::free_(part_sum_); dev::free_(part_max_); dev::free_(stats_dev_);
     comm_.reset();
     for (float* p : integral_) dev::free_(p);
-    dev::free_(lut_dev_); dev::free_(acc_dev_); dev::free_(max_dev_);
+    dev::free_(lut_dev_); dev::free_(acc_dev_); dev::free_(max_dev_); dev::free_(flag_dev_);
     dev::free_(small_buf_); dev::free_(small_khat_);
     conv_.reset();
     tables_.reset();
@@ -486,6 +495,7 @@ void Engine::set_view_host(int v, const float* img, const float* weight) {
     vw.pending = false;
     vw.img = vw.img_owned;
     vw.weight = vw.weight_owned;
+    weights_changed();
 }
 void Engine::set_view_host_async(int v, const float* img, const float* weight) {
     if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
@@ -503,17 +513,19 @@ void Engine::set_view_host_async(int v, const float* img, const float* weight) {
     vw.pending = true;
     vw.img = vw.img_owned;
     vw.weight = vw.weight_owned;
+    weights_changed();
 }
 void Engine::set_view_device(int v, const float* img, const float* weight) {
     if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
     View& vw = views_[v];
     vw.img = img;
-    if (weight) { vw.weight = weight; return; }
+    if (weight) { vw.weight = weight; weights_changed(); return; }
     // weight == nullptr: the weight mask will be generated on the device (mvd_make_blending_weights + mvd_normalize_weights)
     dev::set_device(cfg_.device);
     if (!vw.weight_owned) vw.weight_owned = (float*)dev::alloc(sizeof(float) * local_voxels());
     dev::zero(vw.weight_owned, sizeof(float) * local_voxels(), stream_);
     vw.weight = vw.weight_owned;
+    weights_changed();
 }
 void Engine::set_psf(int v, const float* psf, const int kd[3]) {
     if (v < 0 || v >= cfg_.num_views) throw Error("view index out of range");
@@ -867,6 +879,7 @@ void Engine::make_blending_weights(int v, const int box_min[3], const int box_ma
     if (vw.weight && !vw.weight_owned) throw Error("the weight of this view is borrowed device memory; cannot generate into it");
     if (!vw.weight_owned) vw.weight_owned = (float*)dev::alloc(sizeof(float) * local_voxels());
     vw.weight = vw.weight_owned;
+    weights_changed();
     if (!lut_dev_) {
         const std::vector<double> lut = blend_lut();
         lut_dev_ = (double*)dev::alloc(sizeof(double) * lut.size());
@@ -931,6 +944,7 @@ void Engine::fuse_group_host(int v, const RawViewDev* views_host, int count, con
     dev::free_(dv);
     vw.img = vw.img_owned;
     vw.weight = vw.weight_owned;
+    weights_changed();
 }
 
 void Engine::normalize_view_weights(double osem_speedup, bool additional_smooth, float max_diff_range, float scaling_range) {
@@ -944,6 +958,7 @@ void Engine::normalize_view_weights(double osem_speedup, bool additional_smooth,
         w.w[j] = views_[j].weight_owned;
     }
     normalize_weights(stream_, w, V, (long long)local_voxels(), osem_speedup, additional_smooth, max_diff_range, scaling_range);
+    weights_changed();
 }
 
 void Engine::get_image_host(int v, float* out) {
@@ -1009,8 +1024,13 @@ void Engine::view_update(int v) {
     wait_upload(vw);
     ensure_stats_slot();
     const int nparts = conv_->num_tiles() * conv_->parts_per_tile();
+    const unsigned char* skip = nullptr;
+    if (skip_on_) {
+        if (!skip_valid_) refresh_skip();
+        skip = skip_.data() + (size_t)v * conv_->num_tiles();
+    }
     conv_->view_update(psi_[cur_], psi_[cur_ ^ 1], vw.img, vw.weight, vw.k1hat, vw.k2hat, cfg_.lambda, cfg_.min_value,
-                       vw.max_intensity, part_sum_, part_max_);
+                       vw.max_intensity, part_sum_, part_max_, skip);
     // deterministic two-level reduction of the per-CTA partial statistics
     ReduceParts1 r1{part_sum_, part_max_, nparts, part_sum_ + nparts, part_max_ + nparts};
     pfor(256, r1, stream_);
@@ -1019,6 +1039,47 @@ void Engine::view_update(int v) {
     ++stats_count_;
     cur_ ^= 1;
     if (has_exchange()) exchange_psi(psi_[cur_]);
+}
+
+int Engine::skip_empty_tiles(bool on) {
+    if (!inited_) throw Error("init_views() has not been called");
+    skip_on_ = on;
+    skip_valid_ = false;
+    return on ? refresh_skip() : 0;
+}
+
+int Engine::refresh_skip() {
+    dev::set_device(cfg_.device);
+    const Geometry& g = cfg_.geom;
+    const int V = cfg_.num_views, nt = conv_->num_tiles();
+    if (!flag_dev_) flag_dev_ = (int*)dev::alloc(sizeof(int) * (size_t)V * nt);
+    dev::zero(flag_dev_, sizeof(int) * (size_t)V * nt, stream_);
+    for (int v = 0; v < V; ++v) {
+        View& vw = views_[v];
+        if (!vw.weight) throw Error("view without image/weight");
+        wait_upload(vw);
+        for (int ti = 0; ti < nt; ++ti) {
+            const TileGeom& t = conv_->tiles()[ti];
+            int lo[3], hi[3];
+            for (int d = 0; d < 3; ++d) { lo[d] = t.lo[d] - g.goff[d]; hi[d] = t.hi[d] - g.goff[d]; }
+            box_nonzero(stream_, vw.weight, g.vol[0], g.vol[1], lo, hi, flag_dev_ + (size_t)v * nt + ti);
+        }
+    }
+    std::vector<int> flags((size_t)V * nt);
+    dev::d2h(flags.data(), flag_dev_, sizeof(int) * flags.size(), stream_);
+    dev::sync(stream_);
+    if (cfg_.exchange_scheme == 1 && is_sharded()) {
+        // the neighbours read this box's quotient between the two convolutions: a tile can only be dropped when no rank has content
+        if (!can_reduce()) throw Error("skip_empty_tiles on a sharded scheme-1 context needs the communicator / reduce callback first");
+        std::vector<double> any(flags.begin(), flags.end());
+        all_reduce(any.data(), (int)any.size(), 1);
+        for (size_t i = 0; i < flags.size(); ++i) flags[i] = any[i] > 0.0 ? 1 : 0;
+    }
+    skip_.assign(flags.size(), 0);
+    int skipped = 0;
+    for (size_t i = 0; i < flags.size(); ++i) { skip_[i] = flags[i] ? 0 : 1; skipped += skip_[i]; }
+    skip_valid_ = true;
+    return skipped;
 }
 
 void Engine::comm_attach(std::shared_ptr<NcclComm> comm, int py, int pz) {

@@ -83,8 +83,11 @@ class Convolver {
     // dst(own box) = src (*) kernel, src extended by ext
     void conv(const float* src, float* dst, const cpx* khat, int ext, float ext_value);
     // one fused view update (P1..P9) over all tiles; partial stats -> part_sum/part_max [num_tiles*parts_per_tile]
+    // skip (may be null): one flag per tile; a flagged tile is not computed -- its part of psi is copied unchanged and it reports no change
+    // (a block without content, DeconView.filterBlocksForContent)
     void view_update(const float* psi_in, float* psi_out, const float* img, const float* weight, const cpx* k1hat,
-                     const cpx* k2hat, float lambda, float min_value, float max_intensity, double* part_sum, float* part_max);
+                     const cpx* k2hat, float lambda, float min_value, float max_intensity, double* part_sum, float* part_max,
+                     const unsigned char* skip = nullptr);
     // conv1 -> quotient -> conv2 without the update: the "integral" of one view (P1..P8 + real store), used by the Mul iteration
     void integral(const float* psi_in, const float* img, const cpx* k1hat, const cpx* k2hat, float* integral_out);
     // per-pass CUDA-event timing (bench.py's roofline leg): P1..P9 -> slots 0..8
@@ -111,7 +114,7 @@ class Convolver {
     size_t kdev_cap_ = 0;
     std::function<void(cpx*, const TileGeom&)> mid_exchange_;
     // software L2 prefetch distance in CTAs for the x, y and z passes (MVD_PF_X / MVD_PF_Y / MVD_PF_Z override)
-    int pf_x_ = 74, pf_y_ = 296, pf_z_ = 148;
+    int pf_x_ = 37, pf_y_ = 296, pf_z_ = 0;     // measured (c3, two-stage column plans): the z convolution is 15 % faster without
     int chunk_planes_ = 0;  // planes per L2-resident chunk of the x/y pass chains (0 = whole tile per launch)
     // profiling
     void mark(int pass);
@@ -204,6 +207,8 @@ void psi_fused_stats(stream_t s, const ViewPtrs& vp, int V, float* psi, long lon
 void fill_volume(stream_t s, float* p, long long n, float v);
 void slice_stats(stream_t s, const float* img, const OwnBox& ob, long long nyz, double* acc_dev, float* max_dev);
 void copy_region(stream_t s, const float* src, int sny, int sy0, int sz0, float* dst, int dny, int dy0, int dz0, int nx, int rows, int planes);
+void box_nonzero(stream_t s, const float* w, int nx, int ny, const int lo[3], const int hi[3], int* flag_dev);     // *flag_dev = 1 if any w != 0 in the box
+void clear_parts(stream_t s, double* part_sum, float* part_max, int n);                                            // {0, -1} partial statistics
 void blend_weights(stream_t s, float* out, const double* lut_dev, const int vol[3], const int goff[3], const int box_min[3], const int box_max[3],
                    const float border[3], const float blending[3], const double* inv_affine = nullptr, const int* bbox_offset = nullptr);
 std::vector<double> blend_lut();
@@ -298,6 +303,10 @@ class Engine {
     void exchange_halos();
     int exchange_transport() const { return host_exchange_ ? 2 : (comm_ ? comm_->transport() : -1); }
     void view_update(int v);                               // asynchronous on the engine stream
+    // DeconView.filterBlocksForContent (DeconView.java:204-230): (view, tile) pairs whose weights are all zero inside the tile are not
+    // computed.  Returns how many pairs that currently is (evaluates the weights: synchronises; collective on a sharded scheme-1 context,
+    // where a tile is only dropped when it is empty on every rank because the neighbours need its quotient).
+    int skip_empty_tiles(bool on);
     void fetch_stats(int count, IterStats* out);           // last `count` view updates (synchronises)
     void run_iterations(int n, IterStats* out /* n*V or null */);
     void synchronize() { dev::sync(stream_); }
@@ -369,6 +378,11 @@ class Engine {
     double* acc_dev_ = nullptr;     // {sum, count} scratch
     float* max_dev_ = nullptr;      // per-view maxima scratch
     int stats_cap_ = 0, stats_count_ = 0;
+    bool skip_on_ = false, skip_valid_ = false;
+    std::vector<unsigned char> skip_;   // [view][tile]
+    int* flag_dev_ = nullptr;
+    int refresh_skip();
+    void weights_changed() { skip_valid_ = false; }
 };
 
 // helpers shared with the C ABI

@@ -20,7 +20,8 @@ constexpr int min_blocks_for(size_t smem_bytes, int threads, int want) {
     while (b > 1 && 65536 / (threads * b) < MVD_MIN_REGS) --b;
     return b < 1 ? 1 : b;
 }
-template <class P> constexpr int col_min_blocks() { return min_blocks_for(ColSmem<P>::bytes(), P::THREADS, 3); }
+// radices above 20 keep up to 30 complex values (plus the kernel spectrum in the convolution stage) in registers: two CTAs per SM
+template <class P> constexpr int col_min_blocks() { return min_blocks_for(ColSmem<P>::bytes(), P::THREADS, (P::R1 > 20 || P::R2 > 20 || P::R3 > 20) ? 2 : 3); }
 template <class P> constexpr int x_min_blocks() { return min_blocks_for(XLay<P>::bytes(), P::XTHREADS, (P::R1 > 20 || P::R2 > 20 || P::R3 > 20) ? 3 : 4); }
 
 #ifndef MVD_HOST_EMU
@@ -82,7 +83,7 @@ struct XPersist {
     static constexpr bool ok = (L::PAD == 0) && (P::N % 2 == 0);          // unpadded lines, 16-byte multiples per line
     static constexpr size_t bytes() { return sizeof(cpx) * (2 * L::TILE + L::NTAB) + sizeof(LineInfo) * P::XL + 2 * sizeof(unsigned long long); }
 };
-template <class P> constexpr int xp_min_blocks() { return min_blocks_for(XPersist<P>::bytes(), P::XTHREADS, 3); }
+template <class P> constexpr int xp_min_blocks() { return min_blocks_for(XPersist<P>::bytes(), P::XTHREADS, 4); }
 
 template <class P, int KIND>
 __global__ void __launch_bounds__(P::XTHREADS, xp_min_blocks<P>()) x_kernel_p(const XArgs a) {
@@ -158,6 +159,94 @@ __global__ void __launch_bounds__(P::XTHREADS, xp_min_blocks<P>()) x_kernel_p(co
     if (HAS_OUT && tid == 0) tma::wait_group<0>();
 }
 
+// --------------------------------------------------------------------------------------------
+// Warp-autonomous persistent x-pass kernel (sm_100a): ONE WARP PER LINE.  With XT = 32 lanes along a line every stage of a line's
+// transform can be dealt to the line's own warp, so the phases of a line are separated by __syncwarp() instead of CTA barriers and
+// every warp is an independent pipeline: its own pair of line buffers, its own mbarriers, its own bulk loads (cp.async.bulk ->
+// mbarrier complete_tx) and bulk stores.  Nothing waits for the slowest warp of a CTA any more (the barrier stall was the top stall
+// of the CTA-wide version: 2.3 - 3.5 cycles per issue); the price is the last-stage butterflies running on N / RL of 32 lanes.
+// The CTA only shares the stage twiddle / twist tables.
+// --------------------------------------------------------------------------------------------
+struct WarpExec {
+    double s_;
+    float m_;
+    template <class F> __device__ __forceinline__ void phase(F&& f) { f((int)(threadIdx.x & 31)); __syncwarp(); }
+    __device__ __forceinline__ void stash(int, double s, float m) { s_ = s; m_ = m; }
+    __device__ __forceinline__ void unstash(int, double& s, float& m) { s = s_; m = m_; }
+};
+template <class P, int WPC>
+struct XWarp {
+    using L = XLay<P>;
+    // worth it when the first-stage butterflies fill the warp (N / R1 of 32 lanes; measured: N = 540 with 30 lanes -3 % on the quotient
+    // pass, N = 288 with 18 lanes +35 %)
+    static constexpr bool ok = (L::PAD == 0) && (P::N % 2 == 0) && P::XL == 1 && P::XT == 32 && (P::N / P::R1 >= 28) && (P::N / P::R1 <= 32);
+    static constexpr size_t bytes() {
+        return sizeof(cpx) * (size_t)(2 * WPC * L::LS + L::NTAB) + sizeof(LineInfo) * WPC + 2 * WPC * sizeof(unsigned long long);
+    }
+};
+template <class P, int WPC> constexpr int xw_min_blocks() { return min_blocks_for(XWarp<P, WPC>::bytes(), 32 * WPC, 16 / WPC); }
+
+template <class P, int KIND, int WPC>
+__global__ void __launch_bounds__(32 * WPC, xw_min_blocks<P, WPC>()) x_kernel_w(const XArgs a) {
+    extern __shared__ __align__(128) unsigned char mvd_smem[];
+    using L = XLay<P>;
+    constexpr int M = P::N, THREADS = 32 * WPC;
+    constexpr bool HAS_IN = (KIND != X_FWD), HAS_OUT = (KIND == X_FWD || KIND == X_RATIO);
+    constexpr unsigned LINE_BYTES = (unsigned)(M * sizeof(cpx));
+    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+    cpx* const bufs = reinterpret_cast<cpx*>(mvd_smem);                       // [WPC][2][LS]
+    cpx* const tabs = bufs + 2 * WPC * L::LS;
+    LineInfo* const li_all = reinterpret_cast<LineInfo*>(tabs + L::NTAB);
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(li_all + WPC) + 2 * warp;
+    LineInfo* const li = li_all + warp;
+    cpx* const buf0 = bufs + 2 * warp * L::LS;
+    cpx* const buf1 = buf0 + L::LS;
+
+    for (int i = (int)threadIdx.x; i < L::NTW; i += THREADS) tabs[i] = ld_ro(a.tw + i);
+    if (a.xmode == 0 || KIND == X_RATIO || KIND == X_UPDATE) for (int i = (int)threadIdx.x; i < M; i += THREADS) tabs[L::NTW + i] = ld_ro(a.twist + i);
+    if (HAS_IN && lane == 0) { tma::mbar_init(&bars[0], 1); tma::mbar_init(&bars[1], 1); tma::fence_mbar_init(); }
+    __syncthreads();
+
+    const int nlines = a.line_end - a.line0;
+    const int stride = (int)gridDim.x * WPC;
+    auto issue_load = [&](int ln, cpx* dst, unsigned long long* bar) {   // one lane
+        tma::mbar_expect_tx(bar, LINE_BYTES);
+        tma::load_bulk(dst, a.cdata + (long long)(a.line0 + ln) * a.px, LINE_BYTES, bar);
+    };
+    int ln = (int)blockIdx.x * WPC + warp;
+    if (HAS_IN && lane == 0 && ln < nlines) issue_load(ln, buf0, &bars[0]);
+    unsigned par0 = 0, par1 = 0;
+    WarpExec ex;
+    for (int it = 0; ln < nlines; ln += stride, ++it) {
+        const int b = it & 1;
+        cpx* const sm = b ? buf1 : buf0;
+        // the pass stores into `sm` from its first phase on: the bulk store that last read this buffer (two lines ago) must be done
+        if constexpr (HAS_OUT && !HAS_IN) { if (lane == 0) tma::wait_group_read<1>(); __syncwarp(); }
+        if constexpr (HAS_IN) {
+            if (b) { tma::mbar_wait(&bars[1], par1); par1 ^= 1; } else { tma::mbar_wait(&bars[0], par0); par0 ^= 1; }
+        }
+        auto prefetch_next = [&]() {
+            if constexpr (HAS_IN) {
+                if (lane == 0) {
+                    if constexpr (HAS_OUT) tma::wait_group_read<0>();     // the other buffer's bulk store (previous line) has been read out
+                    const int nl = ln + stride;
+                    if (nl < nlines) issue_load(nl, b ? buf0 : buf1, &bars[b ^ 1]);
+                }
+            }
+        };
+        x_pass_body<P, KIND, WarpExec, true>(ex, a, ln, sm, li, tabs, prefetch_next);
+        if constexpr (HAS_OUT) {
+            tma::fence_proxy_async();                  // generic-proxy writes of the last stage -> visible to the bulk store
+            __syncwarp();
+            if (lane == 0) {
+                tma::store_bulk(a.cdata + (long long)(a.line0 + ln) * a.px, sm, LINE_BYTES);
+                tma::commit_group();
+            }
+        }
+    }
+    if (HAS_OUT && lane == 0) tma::wait_group<0>();
+}
+
 // cudaFuncSetAttribute is a per-device setting: remember which devices of this process already have it (the reference drives several
 // devices from one process, one Java thread each -- MultiViewDeconvolutionSeq.java:92-150)
 inline bool first_use_on_current_device(std::atomic<unsigned long long>& mask) {
@@ -179,9 +268,19 @@ inline int carveout_pref() {   // MVD_CARVEOUT: -1 = driver default, 0..100 = pr
 
 // P: plan of the column (y/z) kernels; PX: plan of the x kernels (same length, its own radices / threading).  The two may differ
 // because the scrambled frequency order of an axis only has to be consistent among the kernels that transform that axis.
-template <class P, class PX>
+// PXP: the x plan of the persistent kernels -- PX with its own number of lines per group (smaller groups = more resident CTAs, i.e. more
+// independent barrier domains per SM; measured on c3: forward / quotient pass -5 / -7 % with 4-line groups, update pass +16 %)
+inline int x_warp_mode() {   // MVD_XWARP=0 selects the CTA-wide persistent kernels (A/B measurements)
+    static const int v = [] { const char* e = std::getenv("MVD_XWARP"); return e ? std::atoi(e) : 1; }();
+    return v;
+}
+
+template <class P, class PX, class PXP>
 struct LenImpl {
+    using PXW = Plan<PX::N, PX::R1, PX::R2, PX::R3, 1, 1, 32, 1>;      // one warp per line
+    static constexpr int WPC = 4;                                      // warps per CTA of the warp-autonomous kernels
     static_assert(P::N == PX::N, "column and x plans must describe the same length");
+    static_assert(PXP::N == PX::N && PXP::R1 == PX::R1 && PXP::R2 == PX::R2 && PXP::R3 == PX::R3 && PXP::XT == PX::XT, "persistent x plan = x plan with another group size");
     static constexpr size_t smem_col = ColSmem<P>::bytes();
     static constexpr size_t smem_x = XLay<PX>::bytes();
     static_assert(sizeof(cpx) * XLay<PX>::TILE >= (sizeof(double) + sizeof(float)) * PX::XTHREADS, "reduction scratch must fit in the tile");
@@ -216,8 +315,11 @@ struct LenImpl {
 #else
         // persistent TMA-staged kernels for the passes that write a complex tile (measured: forward -18 %, quotient -10 %); the update /
         // inverse passes are bound by their real-space loads and keep one line group per CTA (three resident CTAs instead of two)
-        if constexpr (XPersist<PX>::ok && (KIND == X_FWD || KIND == X_RATIO)) {
-            if (x_persistent_enabled()) { xp_persistent<KIND>(a, nblocks, s); return; }
+        if constexpr (XWarp<PXW, WPC>::ok && (KIND == X_FWD || KIND == X_RATIO)) {
+            if (x_persistent_enabled() && x_warp_mode()) { xp_warp<KIND>(a, s); return; }
+        }
+        if constexpr (XPersist<PXP>::ok && (KIND == X_FWD || KIND == X_RATIO)) {
+            if (x_persistent_enabled()) { xp_persistent<KIND>(a, (a.line_end - a.line0 + PXP::XL - 1) / PXP::XL, s); return; }
         }
         static std::atomic<unsigned long long> attr_mask{0};
         if (first_use_on_current_device(attr_mask)) {
@@ -229,28 +331,53 @@ struct LenImpl {
 #endif
     }
 #ifndef MVD_HOST_EMU
-    // persistent launch: one CTA per resident slot of the device (occupancy query on first use), pf_dist = grid size so that the
-    // software L2 prefetch of the real rows targets the line group this CTA handles next
+    // warp-autonomous launch: resident CTAs x WPC warps, every warp strides over the lines of the launch
     template <int KIND>
-    static void xp_persistent(XArgs a, int nblocks, stream_t s) {
-        constexpr size_t smem = XPersist<PX>::bytes();
+    static void xp_warp(XArgs a, stream_t s) {
+        constexpr size_t smem = XWarp<PXW, WPC>::bytes();
         static std::atomic<unsigned long long> attr_mask{0};
         static std::atomic<int> slots[64];
         int d = 0;
         MVD_CUDA_CHECK(cudaGetDevice(&d));
         if (first_use_on_current_device(attr_mask)) {
-            MVD_CUDA_CHECK(cudaFuncSetAttribute(x_kernel_p<PX, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MVD_CUDA_CHECK(cudaFuncSetAttribute(x_kernel_w<PXW, KIND, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 0, sms = 0;
-            MVD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, x_kernel_p<PX, KIND>, PX::XTHREADS, smem));
+            MVD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, x_kernel_w<PXW, KIND, WPC>, 32 * WPC, smem));
+            MVD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d));
+            slots[d & 63] = (per_sm > 0 ? per_sm : 1) * sms;
+        }
+        const int nlines = a.line_end - a.line0;
+        int grid = slots[d & 63].load();
+        if (grid <= 0) grid = 148;
+        if (grid > (nlines + WPC - 1) / WPC) grid = (nlines + WPC - 1) / WPC;
+        if (grid < 1) return;
+        // software L2 prefetch of the real rows: the line this warp handles next (quotient pass; the forward pass is faster without)
+        a.pf_dist = (a.pf_dist > 0 && KIND == X_RATIO) ? grid * WPC : 0;
+        x_kernel_w<PXW, KIND, WPC><<<grid, 32 * WPC, smem, s>>>(a);
+        MVD_CUDA_CHECK(cudaGetLastError());
+    }
+    // persistent launch: one CTA per resident slot of the device (occupancy query on first use), pf_dist = grid size so that the
+    // software L2 prefetch of the real rows targets the line group this CTA handles next
+    template <int KIND>
+    static void xp_persistent(XArgs a, int nblocks, stream_t s) {
+        constexpr size_t smem = XPersist<PXP>::bytes();
+        static std::atomic<unsigned long long> attr_mask{0};
+        static std::atomic<int> slots[64];
+        int d = 0;
+        MVD_CUDA_CHECK(cudaGetDevice(&d));
+        if (first_use_on_current_device(attr_mask)) {
+            MVD_CUDA_CHECK(cudaFuncSetAttribute(x_kernel_p<PXP, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0, sms = 0;
+            MVD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, x_kernel_p<PXP, KIND>, PXP::XTHREADS, smem));
             MVD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d));
             slots[d & 63] = (per_sm > 0 ? per_sm : 1) * sms;
         }
         int grid = slots[d & 63].load();
         if (grid <= 0) grid = 148;
         if (grid > nblocks) grid = nblocks;
-        a.pf_dist = a.pf_dist > 0 ? grid : 0;
+        a.pf_dist = (a.pf_dist > 0 && KIND != X_FWD) ? grid : 0;     // the forward pass is faster without the software prefetch (measured)
         a.nblocks = nblocks;
-        x_kernel_p<PX, KIND><<<grid, PX::XTHREADS, smem, s>>>(a);
+        x_kernel_p<PXP, KIND><<<grid, PXP::XTHREADS, smem, s>>>(a);
         MVD_CUDA_CHECK(cudaGetLastError());
     }
 #endif
@@ -280,5 +407,5 @@ struct LenImpl {
 
 }  // namespace mvd
 
-#define MVD_DEFINE_LEN(N, R1, R2, R3, T, W, XR1, XR2, XR3, XT, XL) \
-    namespace mvd { const LenOps* len_ops_##N() { return LenImpl<Plan<N, R1, R2, R3, T, W, 1, 1>, Plan<N, XR1, XR2, XR3, 1, 1, XT, XL>>::ops(); } }
+#define MVD_DEFINE_LEN(N, R1, R2, R3, T, W, XR1, XR2, XR3, XT, XL, XLP) \
+    namespace mvd { const LenOps* len_ops_##N() { return LenImpl<Plan<N, R1, R2, R3, T, W, 1, 1>, Plan<N, XR1, XR2, XR3, 1, 1, XT, XL>, Plan<N, XR1, XR2, XR3, 1, 1, XT, XLP>>::ops(); } }

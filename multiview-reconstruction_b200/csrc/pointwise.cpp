@@ -166,6 +166,28 @@ void copy_region(stream_t s, const float* src, int sny, int sy0, int sz0, float*
     pfor((long long)nx * rows * planes, CopyRegion{src, dst, nx, rows, sny, sy0, sz0, dny, dy0, dz0}, s);
 }
 
+// DeconView.blockContainsContent (M/process/deconvolution/DeconView.java:232-274): does the weight volume hold a value != 0 inside a box
+// (local coordinates, half open)?  flag is set to 1 by every thread that finds one (the same value from all writers).
+struct BoxNonZero {
+    const float* w; int nx, ny; int x0, y0, z0, bx, by; int* flag;
+    MVD_HD void operator()(long long i) const {
+        const int x = (int)(i % bx);
+        const long long r = i / bx;
+        const int y = (int)(r % by), z = (int)(r / by);
+        if (w[((long long)(z0 + z) * ny + (y0 + y)) * nx + (x0 + x)] != 0.f) *flag = 1;
+    }
+};
+void box_nonzero(stream_t s, const float* w, int nx, int ny, const int lo[3], const int hi[3], int* flag_dev) {
+    const int bx = hi[0] - lo[0], by = hi[1] - lo[1], bz = hi[2] - lo[2];
+    if (bx <= 0 || by <= 0 || bz <= 0) return;
+    pfor((long long)bx * by * bz, BoxNonZero{w, nx, ny, lo[0], lo[1], lo[2], bx, by, flag_dev}, s);
+}
+struct FillParts {
+    double* ps; float* pm;
+    MVD_HD void operator()(long long i) const { ps[i] = 0.0; pm[i] = -1.f; }
+};
+void clear_parts(stream_t s, double* part_sum, float* part_max, int n) { pfor(n, FillParts{part_sum, part_max}, s); }
+
 // ---------------------------------------------------------------------------------------------------------------------
 // BlendingRealRandomAccess.computeWeight (M/process/fusion/transformed/weights/BlendingRealRandomAccess.java:95-130) for an
 // axis-aligned box on the integer grid; lut = the 1001-entry cosine table built exactly like the reference's static initialiser.

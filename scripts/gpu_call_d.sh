@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( timeout 300 bash scripts/sweep_env.sh MVD_XWARP "1 0" c3 2
+  timeout 300 bash scripts/sweep_env.sh MVD_PF_Y "0 74 148" c3 2
+  timeout 200 bash scripts/sweep_env.sh MVD_PF_Z "0" c3 2 ) 2>&1 | tee gpurun_out/ab_d.txt
+timeout 300 python bench.py --skip-e2e --skip-cpu --steps 5 --warmup 3 > gpurun_out/d_bench_c3.json 2> gpurun_out/d_bench_c3.err; tail -c 1200 gpurun_out/d_bench_c3.json; tail -3 gpurun_out/d_bench_c3.err
+timeout 300 python bench.py --config c2 --skip-e2e --skip-cpu --steps 5 --warmup 3 > gpurun_out/d_bench_c2.json 2> gpurun_out/d_bench_c2.err; tail -c 600 gpurun_out/d_bench_c2.json; tail -3 gpurun_out/d_bench_c2.err

@@ -255,3 +255,51 @@ def check_tiff_io_and_psi_init_from_file(lib, oracle, small_dataset, tmp_path):
         assert not m.MultiViewDeconvolutionSeq(dv, 0, m.PsiInitFromFile(str(tmp_path / "missing.tif"), True)).initWasSuccessful()
     finally:
         dv.close()
+
+
+def check_skip_empty_tiles(lib, oracle):
+    """DeconView.filterBlocksForContent on the resident path: tiles in which a view has no weight are not computed; the result and the
+    statistics are those of the unfiltered run (a zero weight leaves psi untouched, DeconvolutionMethods.java:356)."""
+    import mvrecon_b200 as m
+    ds = oracle.make_synthetic((64, 36, 40), 2, seed=5, psf_size_xyz=(5, 5, 7), psf_sigma_xyz=(1.0, 1.0, 1.6), bead_density=1024)
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN)
+    mx = [v.max_intensity for v in views]
+    weights = [w.copy() for w in ds.weights]
+    weights[0][20:] = 0.0                               # view 0 contributes nothing to the upper part of the volume
+    results = []
+    for on in (False, True):
+        dv = m.DeconViews([m.DeconView(ds.images[v], weights[v], ds.psfs[v], m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(2)],
+                          max_fft_len=48, library=lib)
+        try:
+            assert dv.tile_info()["num_tiles"] >= 2
+            dec = m.MultiViewDeconvolutionSeq(dv, 2, m.PsiInitFromRAI(psi0, mx))
+            skipped = dv.filterBlocksForContent(on)
+            assert (skipped >= 1) if on else (skipped == 0)
+            dec.runIterations()
+            results.append((dec.getPSI(), [(s.sumChange, s.maxChange) for it in dec.stats for s in it], skipped))
+            if on:                                       # a change of the weights re-evaluates the filter
+                dv.lib.check(dv.lib.dll.mvd_set_view(dv._ctx, 0, m._fp(ds.images[0]), m._fp(ds.weights[0])))
+                assert dv.filterBlocksForContent(True) == 0
+        finally:
+            dv.close()
+    assert np.array_equal(results[0][0], results[1][0])
+    for a, b in zip(results[0][1], results[1][1]):
+        assert abs(a[0] - b[0]) <= 1e-9 * max(1.0, abs(a[0])) and a[1] == b[1]
+    ov = [oracle.OracleView(ds.images[v], weights[v], views[v].kernel1, views[v].kernel2, mx[v]) for v in range(2)]
+    ref, _ = oracle.run_iterations_seq(psi0, ov, 2, 0.0, dtype=np.float64)
+    assert oracle.rel_l2(results[1][0], ref) < 4e-6
+
+
+def check_filter_blocks_mirror():
+    """Python mirror of DeconView.filterBlocksForContent / blockContainsContent (DeconView.java:204-274) used by the L2 block driver."""
+    import mvrecon_b200 as m
+    w = np.zeros((40, 36, 32), dtype=np.float32)
+    w[:10, :, :] = 1.0
+    blocks = m.divideIntoBlocks((32, 36, 40), (32, 32, 32), (9, 9, 9))
+    batches = m.sortBlocksBySmallestFootprint(blocks, (32, 36, 40))
+    n_before = sum(len(b) for b in batches)
+    expect_keep = sum(1 for b in blocks if b.offset[2] < 10 and b.offset[2] + b.blockSize[2] > 0)
+    removed, removed_batches = m.filterBlocksForContent(batches, w)
+    assert removed == n_before - expect_keep and removed > 0
+    assert sum(len(b) for b in batches) == expect_keep and all(len(b) > 0 for b in batches)
+    assert all(m.blockContainsContent(b, w) for batch in batches for b in batch)

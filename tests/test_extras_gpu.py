@@ -35,3 +35,11 @@ def test_fuse_group(product_lib, oracle, interpolation, with_blending):
 
 def test_psf_preparation(product_lib, oracle):
     X.check_psf_preparation(product_lib, oracle)
+
+
+def test_skip_empty_tiles(product_lib, oracle):
+    X.check_skip_empty_tiles(product_lib, oracle)
+
+
+def test_tiff_io_and_psi_init_from_file(product_lib, oracle, small_dataset, tmp_path):
+    X.check_tiff_io_and_psi_init_from_file(product_lib, oracle, small_dataset, tmp_path)

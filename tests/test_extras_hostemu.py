@@ -37,3 +37,11 @@ def test_psf_preparation(hostemu_lib, oracle):
 
 def test_tiff_io_and_psi_init_from_file(hostemu_lib, oracle, small_dataset, tmp_path):
     X.check_tiff_io_and_psi_init_from_file(hostemu_lib, oracle, small_dataset, tmp_path)
+
+
+def test_skip_empty_tiles(hostemu_lib, oracle):
+    X.check_skip_empty_tiles(hostemu_lib, oracle)
+
+
+def test_filter_blocks_mirror():
+    X.check_filter_blocks_mirror()
