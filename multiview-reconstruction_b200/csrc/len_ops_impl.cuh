@@ -74,6 +74,10 @@ __device__ __forceinline__ void store_bulk(void* dst, const void* src, unsigned 
 __device__ __forceinline__ void commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// L2 prefetch of a contiguous range through the bulk-copy unit: ONE instruction per row instead of one per 128 bytes
+__device__ __forceinline__ void prefetch_bulk_l2(const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 }  // namespace tma
 
@@ -214,12 +218,32 @@ __global__ void __launch_bounds__(32 * WPC, xw_min_blocks<P, WPC>()) x_kernel_w(
         tma::load_bulk(dst, a.cdata + (long long)(a.line0 + ln) * a.px, LINE_BYTES, bar);
     };
     int ln = (int)blockIdx.x * WPC + warp;
-    if (HAS_IN && lane == 0 && ln < nlines) issue_load(ln, buf0, &bars[0]);
     unsigned par0 = 0, par1 = 0;
     WarpExec ex;
-    for (int it = 0; ln < nlines; ln += stride, ++it) {
+    // x range of the real rows this tile reads, as a 16-byte aligned byte range (bulk prefetch granularity); rows start 16-byte aligned
+    // when the local x extent is a multiple of 4
+    int pf_x0 = clampi(a.org[0] - a.goff[0], 0, a.vol[0] - 1) & ~3;
+    int pf_x1 = clampi(a.org[0] - a.goff[0] + 2 * M, 0, a.vol[0]);
+    const unsigned pf_bytes = (unsigned)((pf_x1 - pf_x0) * 4) & ~15u;
+    const bool pf_rows = a.pf_dist > 0 && (a.vol[0] & 3) == 0 && ((reinterpret_cast<unsigned long long>(a.src) & 15ull) == 0) && pf_bytes > 0;
+    // lines outside the responsibility box of the update / inverse pass are skipped (no load, no work)
+    auto has_work = [&](int l) -> bool {
+        if constexpr (KIND == X_UPDATE || KIND == X_INV) return x_line_in_box(a, a.line0 + l);
+        else return true;
+    };
+    if constexpr (KIND == X_UPDATE || KIND == X_INV) {
+        while (ln < nlines && !has_work(ln)) ln += stride;
+    }
+    if (HAS_IN && lane == 0 && ln < nlines) issue_load(ln, buf0, &bars[0]);
+    double wsum = 0.0;
+    float wmax = -1.f;
+    for (int it = 0; ln < nlines; ++it) {
         const int b = it & 1;
         cpx* const sm = b ? buf1 : buf0;
+        int nl = ln + stride;
+        if constexpr (KIND == X_UPDATE || KIND == X_INV) {
+            while (nl < nlines && !has_work(nl)) nl += stride;
+        }
         // the pass stores into `sm` from its first phase on: the bulk store that last read this buffer (two lines ago) must be done
         if constexpr (HAS_OUT && !HAS_IN) { if (lane == 0) tma::wait_group_read<1>(); __syncwarp(); }
         if constexpr (HAS_IN) {
@@ -229,8 +253,20 @@ __global__ void __launch_bounds__(32 * WPC, xw_min_blocks<P, WPC>()) x_kernel_w(
             if constexpr (HAS_IN) {
                 if (lane == 0) {
                     if constexpr (HAS_OUT) tma::wait_group_read<0>();     // the other buffer's bulk store (previous line) has been read out
-                    const int nl = ln + stride;
-                    if (nl < nlines) issue_load(nl, b ? buf0 : buf1, &bars[b ^ 1]);
+                    if (nl < nlines) {
+                        issue_load(nl, b ? buf0 : buf1, &bars[b ^ 1]);
+                        if constexpr (KIND == X_RATIO || KIND == X_UPDATE) {
+                            // observed-image row of that line -> L2 (one bulk prefetch; rows outside the volume carry no data)
+                            const int l = a.line0 + nl;
+                            const int gy = a.org[1] + l % a.ty, gz = a.org[2] + l / a.ty;
+                            if (pf_rows && (unsigned)gy < (unsigned)a.gdim[1] && (unsigned)gz < (unsigned)a.gdim[2]) {
+                                const int ly = clampi(gy - a.goff[1], 0, a.vol[1] - 1), lz = clampi(gz - a.goff[2], 0, a.vol[2] - 1);
+                                const float* p = a.src + ((long long)lz * a.vol[1] + ly) * (long long)a.vol[0] + pf_x0;
+                                tma::prefetch_bulk_l2(p, pf_bytes);
+                                if constexpr (KIND == X_UPDATE) tma::prefetch_bulk_l2(a.weight + (p - a.src), pf_bytes);
+                            }
+                        }
+                    }
                 }
             }
         };
@@ -243,8 +279,25 @@ __global__ void __launch_bounds__(32 * WPC, xw_min_blocks<P, WPC>()) x_kernel_w(
                 tma::commit_group();
             }
         }
+        if constexpr (KIND == X_UPDATE) {              // signed change statistics of this lane's voxels, kept in registers across the lines
+            double s; float m;
+            ex.unstash(lane, s, m);
+            wsum += s; wmax = m > wmax ? m : wmax;
+        }
+        ln = nl;
     }
     if (HAS_OUT && lane == 0) tma::wait_group<0>();
+    if constexpr (KIND == X_UPDATE) {
+        // warp-shuffle reduction (fixed tree: deterministic), one partial per warp; the remaining slots of the launch are neutral
+        for (int o = 16; o > 0; o >>= 1) {
+            wsum += __shfl_down_sync(0xffffffffu, wsum, o);
+            const float om = __shfl_down_sync(0xffffffffu, wmax, o);
+            wmax = om > wmax ? om : wmax;
+        }
+        const int gw = (int)blockIdx.x * WPC + warp;
+        if (lane == 0) { a.part_sum[gw] = wsum; a.part_max[gw] = wmax; }
+        for (int i = stride + (int)blockIdx.x * THREADS + (int)threadIdx.x; i < a.nblocks; i += (int)gridDim.x * THREADS) { a.part_sum[i] = 0.0; a.part_max[i] = -1.f; }
+    }
 }
 
 // cudaFuncSetAttribute is a per-device setting: remember which devices of this process already have it (the reference drives several
@@ -315,8 +368,12 @@ struct LenImpl {
 #else
         // persistent TMA-staged kernels for the passes that write a complex tile (measured: forward -18 %, quotient -10 %); the update /
         // inverse passes are bound by their real-space loads and keep one line group per CTA (three resident CTAs instead of two)
-        if constexpr (XWarp<PXW, WPC>::ok && (KIND == X_FWD || KIND == X_RATIO)) {
-            if (x_persistent_enabled() && x_warp_mode()) { xp_warp<KIND>(a, s); return; }
+        if constexpr (XWarp<PXW, WPC>::ok) {
+            // MVD_XWARP: 1 (default) = forward / quotient passes; 2 = update / inverse passes too (measured on c3: update pass 0.91 ms against
+            // 0.83 ms of the one-shot kernel -- 124 registers leave 16 warps per SM where the one-shot kernel has 24 to hide its row loads)
+            if (x_persistent_enabled() && (x_warp_mode() >= 2 || (x_warp_mode() == 1 && (KIND == X_FWD || KIND == X_RATIO)))) {
+                if (xp_warp<KIND>(a, nblocks, s)) return;
+            }
         }
         if constexpr (XPersist<PXP>::ok && (KIND == X_FWD || KIND == X_RATIO)) {
             if (x_persistent_enabled()) { xp_persistent<KIND>(a, (a.line_end - a.line0 + PXP::XL - 1) / PXP::XL, s); return; }
@@ -333,7 +390,7 @@ struct LenImpl {
 #ifndef MVD_HOST_EMU
     // warp-autonomous launch: resident CTAs x WPC warps, every warp strides over the lines of the launch
     template <int KIND>
-    static void xp_warp(XArgs a, stream_t s) {
+    static bool xp_warp(XArgs a, int nblocks, stream_t s) {
         constexpr size_t smem = XWarp<PXW, WPC>::bytes();
         static std::atomic<unsigned long long> attr_mask{0};
         static std::atomic<int> slots[64];
@@ -350,11 +407,14 @@ struct LenImpl {
         int grid = slots[d & 63].load();
         if (grid <= 0) grid = 148;
         if (grid > (nlines + WPC - 1) / WPC) grid = (nlines + WPC - 1) / WPC;
-        if (grid < 1) return;
-        // software L2 prefetch of the real rows: the line this warp handles next (quotient pass; the forward pass is faster without)
-        a.pf_dist = (a.pf_dist > 0 && KIND == X_RATIO) ? grid * WPC : 0;
+        if (grid < 1) return true;
+        if (KIND == X_UPDATE && grid * WPC > nblocks) return false;      // one statistics slot per warp
+        a.nblocks = nblocks;
+        // bulk L2 prefetch of the real rows of the line a warp handles next (the forward pass is faster without)
+        a.pf_dist = (a.pf_dist > 0 && KIND != X_FWD) ? grid * WPC : 0;
         x_kernel_w<PXW, KIND, WPC><<<grid, 32 * WPC, smem, s>>>(a);
         MVD_CUDA_CHECK(cudaGetLastError());
+        return true;
     }
     // persistent launch: one CTA per resident slot of the device (occupancy query on first use), pf_dist = grid size so that the
     // software L2 prefetch of the real rows targets the line group this CTA handles next
