@@ -421,18 +421,29 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     if os.environ.get("BENCH_EXCHANGE_ONLY") and world > 1:          # development: cost of the bare psi halo exchange
-        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # BENCH_EXCHANGE_GAP_US: busy-wait of that length on the compute stream before every exchange (what a pass kernel does to the
+        # links: they sit idle in between) -- exchange time is then measured per exchange, gaps excluded
+        gap_us = float(os.environ.get("BENCH_EXCHANGE_GAP_US", "0"))
+        cycles = int(gap_us * 1.9e3)
+        n_ex = 50
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_ex)]
         for _ in range(5):
             dv.exchange_halos()
         dv.synchronize(); dist.barrier()
-        ea.record(stream)
-        for _ in range(50):
+        for a, b in evs:
+            if cycles:
+                with torch.cuda.stream(stream):
+                    torch.cuda._sleep(cycles)
+            a.record(stream)
             dv.exchange_halos()
-        eb.record(stream); eb.synchronize()
-        t = torch.tensor([ea.elapsed_time(eb) / 50 * 1e3], device=f"cuda:{local}")
+            b.record(stream)
+        evs[-1][1].synchronize()
+        per = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
+        t = torch.tensor([sum(per) / n_ex, per[n_ex // 2], per[0], per[-1]], device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(json.dumps({"exchange_only_us": float(t.item()), "transport": transport, "grid": [py, pz], "halo": [Hy, Hz],
+            print(json.dumps({"exchange_only_us": float(t[0].item()), "median_us": float(t[1].item()), "min_us": float(t[2].item()),
+                              "max_us": float(t[3].item()), "gap_us": gap_us, "transport": transport, "grid": [py, pz], "halo": [Hy, Hz],
                               "local_box_zyx": list(local_shape)}))
         dv.close(); dist.barrier(); dist.destroy_process_group()
         return
@@ -453,10 +464,17 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     pass_ms, pass_n = dv.pass_times(reset=True)
     dv.set_profiling(False)
+    rank_pass_ms = None
     if world > 1:
         t = torch.tensor([ms], device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        # time every rank spent inside its nine passes per step (CUDA events around the launches): the rest of the step is exchange + waiting
+        # for the slowest neighbour
+        mine = torch.zeros(world, device=f"cuda:{local}")
+        mine[rank] = sum(pass_ms) / max(args.steps, 1)
+        dist.all_reduce(mine)
+        rank_pass_ms = [round(float(x), 3) for x in mine.tolist()]
     vox = nz * ny * nx
     value = vox * V * args.steps / (ms * 1e-3)
 
@@ -514,7 +532,7 @@ def run_ours(args):
         if rank == 0:
             print(json.dumps({"metric": "voxel*view*iterations/s", "value": value, "n_gpus": world, "ms_per_step": ms / args.steps,
                               "note": "profiling run (--skip-e2e): not a bench line", "transport": transport, "parity": parity,
-                              "fft_tile_xyz": info["tile_dims_xyz"], "tiles_per_gpu": info["num_tiles"],
+                              "fft_tile_xyz": info["tile_dims_xyz"], "tiles_per_gpu": info["num_tiles"], "pass_ms_per_step_by_rank": rank_pass_ms,
                               "all_passes_ms_per_launch": [round(a / max(b, 1), 4) for a, b in zip(pass_ms, pass_n)]}))
         if comm is not None:
             comm.close()
@@ -596,6 +614,8 @@ def run_ours(args):
                     "what": "DeconViews(page-locked host images, async upload on a copy stream) + device weight masks + PSF->kernel derivation + spectra + PsiInit + iterations + getPSI(), wall clock; bytes amortised per iteration"},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if rank_pass_ms is not None:
+            line["pass_ms_per_step_by_rank"] = rank_pass_ms      # the step minus this = halo exchange + waiting for the slowest neighbour
         print(json.dumps(line), flush=True)
     if comm is not None:
         comm.close()

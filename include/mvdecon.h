@@ -93,7 +93,8 @@ typedef struct mvd_config {
      * chained convolutions (k1/2 + k2/2) and the box recomputes the neighbour's quotient there.  1 (B): two exchanges -- psi by the
      * reach of kernel1 before the update, and between the two convolutions the quotient (as the rows / planes of its x-spectrum) by
      * the reach of kernel2; interior sides carry max(k1/2, k2/2) only, i.e. less redundant FFT volume.  Scheme 1 needs an attached
-     * exchange (mvd_comm_attach or mvd_set_exchange_callback), one FFT tile per context, and does not support the Mul iteration.   */
+     * exchange (mvd_comm_attach or mvd_set_exchange_callback), a box that fits one FFT tile in y and z (several tiles may follow each other
+     * along x), and does not support the Mul iteration.                                                                            */
     int exchange_scheme;
 } mvd_config;
 

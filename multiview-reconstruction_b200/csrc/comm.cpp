@@ -81,6 +81,13 @@ static void pack_rows(const HaloBox& b, float* stage, int ya, int rows, int to_s
     }
 }
 
+// whole planes [za, za + planes) <-> dense staging, scalar granules (the fallback for boxes whose planes are not 16-byte multiples)
+static void pack_planes(const HaloBox& b, float* stage, int za, int planes, int to_stage, stream_t s) {
+    if (planes <= 0) return;
+    PackRows<float> p{b.base, stage, b.row_floats, b.nrows, 0, za, b.nrows, to_stage};
+    pfor((long long)b.nrows * b.row_floats * planes, p, s);
+}
+
 void NcclComm::unique_id(char out[128]) {
 #ifndef MVD_HOST_EMU
     ncclUniqueId id;
@@ -246,7 +253,7 @@ struct AwaitArrival {
             if (!f) continue;
             while ((int)(*f - seq) < 0) {
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                if (t - t0 > 30000000000ULL) __trap();            // a neighbour died: fail loudly instead of hanging the device
+                if (t - t0 > 120000000000ULL) __trap();           // a neighbour died: fail loudly instead of hanging the device
                 __nanosleep(64);
             }
         }
@@ -261,6 +268,78 @@ struct CopyQuads {
 
 #ifndef MVD_HOST_EMU
 namespace {
+// One halo slab as rows [ya, ya + rows) x planes [za, za + planes) of a [.][ny][nx4] volume of 16-byte granules and its dense image
+// in a landing buffer (z slabs: all rows of whole planes).
+struct HaloSeg {
+    Quad* vol; Quad* stage; long long nx4, count; int ny, ya, za, rows;
+    __device__ __forceinline__ long long vol_index(long long i) const {
+        const long long x = i % nx4, r = i / nx4;
+        const int y = (int)(r % rows), z = (int)(r / rows);
+        return ((long long)(za + z) * ny + (ya + y)) * nx4 + x;
+    }
+};
+inline HaloSeg make_seg(const HaloBox& b, float* stage, int ya, int rows, int za, int planes) {
+    HaloSeg s;
+    s.vol = (Quad*)b.base; s.stage = (Quad*)stage; s.nx4 = b.row_floats / 4; s.ny = b.nrows; s.ya = ya; s.za = za; s.rows = rows;
+    s.count = (rows > 0 && planes > 0) ? s.nx4 * rows * planes : 0;
+    return s;
+}
+inline unsigned long long exchange_timeout_ns() {      // MVD_EXCHANGE_TIMEOUT_S: watchdog of the arrival wait (default 120 s, 0 = wait forever)
+    static const unsigned long long v = [] {
+        const char* e = std::getenv("MVD_EXCHANGE_TIMEOUT_S");
+        return (unsigned long long)(e ? std::atof(e) : 120.0) * 1000000000ULL;
+    }();
+    return v;
+}
+// push: both slabs of one exchange phase go straight into the neighbours' landing buffers (remote stores over NVLink); the CTA that
+// finishes last releases the neighbours' arrival flags -- pack, pack, signal, signal in ONE launch.
+__global__ void __launch_bounds__(256) halo_push_kernel(HaloSeg s0, HaloSeg s1, unsigned* flag0, unsigned* flag1, unsigned seq, unsigned* done) {
+    const long long n = s0.count + s1.count;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (i < s0.count) s0.stage[i] = s0.vol[s0.vol_index(i)];
+        else { const long long k = i - s0.count; s1.stage[k] = s1.vol[s1.vol_index(k)]; }
+    }
+    __threadfence_system();                 // this thread's remote stores are performed before its CTA reports in
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1) {        // every CTA of the launch has stored (and fenced) its part
+            *done = 0;
+            __threadfence_system();
+            if (flag0) *(volatile unsigned*)flag0 = seq;
+            if (flag1) *(volatile unsigned*)flag1 = seq;
+        }
+    }
+}
+// pull: wait for the neighbours' arrival flags, then unpack both landing buffers -- await, unpack, unpack in ONE launch
+__global__ void __launch_bounds__(256) halo_pull_kernel(HaloSeg s0, HaloSeg s1, const unsigned* f0, const unsigned* f1, unsigned seq,
+                                                        unsigned long long timeout_ns) {
+    if (threadIdx.x == 0) {
+        unsigned long long t0, t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (int k = 0; k < 2; ++k) {
+            const volatile unsigned* f = k == 0 ? f0 : f1;
+            if (!f) continue;
+            while ((int)(*f - seq) < 0) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (timeout_ns && t - t0 > timeout_ns) __trap();      // a neighbour died: fail loudly instead of hanging the device
+                __nanosleep(32);
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const long long n = s0.count + s1.count;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (i < s0.count) s0.vol[s0.vol_index(i)] = s0.stage[i];
+        else { const long long k = i - s0.count; s1.vol[s1.vol_index(k)] = s1.stage[k]; }
+    }
+}
+inline int halo_grid(long long n) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
 struct PeerInfo {
     cudaIpcMemHandle_t handle;
     unsigned long long pid, ptr, need_y, need_z;
@@ -357,34 +436,54 @@ void HaloComm::exchange_peer(const HaloBox& b) {
     ++seq_;
     const int par = (int)(seq_ & 1u);
     unsigned* mine = flags(region_);
+    unsigned* done = mine + 16;                           // launch-local CTA counter of the push kernels (returns to 0 after every launch)
+    const bool quads = b.row_floats % 4 == 0 && ((uintptr_t)b.base % 16) == 0;
+    const unsigned long long tmo = exchange_timeout_ns();
     if (py_ > 1 && (b.hy_lo > 0 || b.hy_hi > 0)) {
         const bool lower = ry_ > 0, upper = ry_ < py_ - 1;
-        const size_t per_row = (size_t)b.row_floats * (size_t)(b.z1 - b.z0);
+        const int planes = b.z1 - b.z0;
+        const size_t per_row = (size_t)b.row_floats * (size_t)planes;
         if ((size_t)std::max(b.hy_lo, b.hy_hi) * per_row > cap_y_) throw Error("halo exchange: landing buffer too small (y)");
         // I am the lower neighbour's UPPER neighbour: my first hy_hi own rows land in its "from upper y" buffer (src 1), and vice versa
-        if (lower) { pack_rows(b, landing(nb_region_[0], 1, par), b.y0, b.hy_hi, 1, stream_); pfor(1, SignalArrival{flags(nb_region_[0]) + 1, seq_}, stream_); }
-        if (upper) { pack_rows(b, landing(nb_region_[1], 0, par), b.y1 - b.hy_lo, b.hy_lo, 1, stream_); pfor(1, SignalArrival{flags(nb_region_[1]) + 0, seq_}, stream_); }
-        if (lower || upper) pfor(1, AwaitArrival{lower ? mine + 0 : nullptr, upper ? mine + 1 : nullptr, seq_}, stream_);
-        if (lower) pack_rows(b, landing(region_, 0, par), b.y0 - b.hy_lo, b.hy_lo, 0, stream_);
-        if (upper) pack_rows(b, landing(region_, 1, par), b.y1, b.hy_hi, 0, stream_);
+        if (quads && (lower || upper)) {
+            HaloSeg p0 = make_seg(b, lower ? landing(nb_region_[0], 1, par) : nullptr, b.y0, lower ? b.hy_hi : 0, b.z0, planes);
+            HaloSeg p1 = make_seg(b, upper ? landing(nb_region_[1], 0, par) : nullptr, b.y1 - b.hy_lo, upper ? b.hy_lo : 0, b.z0, planes);
+            halo_push_kernel<<<halo_grid(p0.count + p1.count), 256, 0, stream_>>>(p0, p1, lower ? flags(nb_region_[0]) + 1 : nullptr,
+                                                                                   upper ? flags(nb_region_[1]) + 0 : nullptr, seq_, done);
+            HaloSeg u0 = make_seg(b, lower ? landing(region_, 0, par) : nullptr, b.y0 - b.hy_lo, lower ? b.hy_lo : 0, b.z0, planes);
+            HaloSeg u1 = make_seg(b, upper ? landing(region_, 1, par) : nullptr, b.y1, upper ? b.hy_hi : 0, b.z0, planes);
+            halo_pull_kernel<<<halo_grid(u0.count + u1.count), 256, 0, stream_>>>(u0, u1, lower ? mine + 0 : nullptr, upper ? mine + 1 : nullptr, seq_, tmo);
+            MVD_CUDA_CHECK(cudaGetLastError());
+        } else {
+            if (lower) { pack_rows(b, landing(nb_region_[0], 1, par), b.y0, b.hy_hi, 1, stream_); pfor(1, SignalArrival{flags(nb_region_[0]) + 1, seq_}, stream_); }
+            if (upper) { pack_rows(b, landing(nb_region_[1], 0, par), b.y1 - b.hy_lo, b.hy_lo, 1, stream_); pfor(1, SignalArrival{flags(nb_region_[1]) + 0, seq_}, stream_); }
+            if (lower || upper) pfor(1, AwaitArrival{lower ? mine + 0 : nullptr, upper ? mine + 1 : nullptr, seq_}, stream_);
+            if (lower) pack_rows(b, landing(region_, 0, par), b.y0 - b.hy_lo, b.hy_lo, 0, stream_);
+            if (upper) pack_rows(b, landing(region_, 1, par), b.y1, b.hy_hi, 0, stream_);
+        }
     }
     if (pz_ > 1 && (b.hz_lo > 0 || b.hz_hi > 0)) {
         const bool lower = rz_ > 0, upper = rz_ < pz_ - 1;
         const size_t plane = (size_t)b.row_floats * (size_t)b.nrows;
         if (plane * (size_t)std::max(b.hz_lo, b.hz_hi) > cap_z_) throw Error("halo exchange: landing buffer too small (z)");
-        if (plane % 4 != 0 || ((uintptr_t)b.base % 16) != 0) throw Error("halo exchange: unaligned planes");
-        const long long q_lo = (long long)(plane * b.hz_lo / 4), q_hi = (long long)(plane * b.hz_hi / 4);
-        if (lower) {
-            pfor(q_hi, CopyQuads{(const Quad*)(b.base + plane * b.z0), (Quad*)landing(nb_region_[2], 3, par)}, stream_);
-            pfor(1, SignalArrival{flags(nb_region_[2]) + 3, seq_}, stream_);
+        if (quads && (lower || upper)) {                   // whole planes including the fresh y halos: all rows
+            HaloSeg p0 = make_seg(b, lower ? landing(nb_region_[2], 3, par) : nullptr, 0, b.nrows, b.z0, lower ? b.hz_hi : 0);
+            HaloSeg p1 = make_seg(b, upper ? landing(nb_region_[3], 2, par) : nullptr, 0, b.nrows, b.z1 - b.hz_lo, upper ? b.hz_lo : 0);
+            halo_push_kernel<<<halo_grid(p0.count + p1.count), 256, 0, stream_>>>(p0, p1, lower ? flags(nb_region_[2]) + 3 : nullptr,
+                                                                                   upper ? flags(nb_region_[3]) + 2 : nullptr, seq_, done);
+            HaloSeg u0 = make_seg(b, lower ? landing(region_, 2, par) : nullptr, 0, b.nrows, b.z0 - b.hz_lo, lower ? b.hz_lo : 0);
+            HaloSeg u1 = make_seg(b, upper ? landing(region_, 3, par) : nullptr, 0, b.nrows, b.z1, upper ? b.hz_hi : 0);
+            halo_pull_kernel<<<halo_grid(u0.count + u1.count), 256, 0, stream_>>>(u0, u1, lower ? mine + 2 : nullptr, upper ? mine + 3 : nullptr, seq_, tmo);
+            MVD_CUDA_CHECK(cudaGetLastError());
+        } else {
+            // scalar path for boxes whose rows are not 16-byte granules (arbitrary bounding boxes): whole planes as dense rows
+            const HaloBox pb = b;
+            if (lower) { pack_planes(pb, landing(nb_region_[2], 3, par), b.z0, b.hz_hi, 1, stream_); pfor(1, SignalArrival{flags(nb_region_[2]) + 3, seq_}, stream_); }
+            if (upper) { pack_planes(pb, landing(nb_region_[3], 2, par), b.z1 - b.hz_lo, b.hz_lo, 1, stream_); pfor(1, SignalArrival{flags(nb_region_[3]) + 2, seq_}, stream_); }
+            if (lower || upper) pfor(1, AwaitArrival{lower ? mine + 2 : nullptr, upper ? mine + 3 : nullptr, seq_}, stream_);
+            if (lower) pack_planes(pb, landing(region_, 2, par), b.z0 - b.hz_lo, b.hz_lo, 0, stream_);
+            if (upper) pack_planes(pb, landing(region_, 3, par), b.z1, b.hz_hi, 0, stream_);
         }
-        if (upper) {
-            pfor(q_lo, CopyQuads{(const Quad*)(b.base + plane * (b.z1 - b.hz_lo)), (Quad*)landing(nb_region_[3], 2, par)}, stream_);
-            pfor(1, SignalArrival{flags(nb_region_[3]) + 2, seq_}, stream_);
-        }
-        if (lower || upper) pfor(1, AwaitArrival{lower ? mine + 2 : nullptr, upper ? mine + 3 : nullptr, seq_}, stream_);
-        if (lower) pfor(q_lo, CopyQuads{(const Quad*)landing(region_, 2, par), (Quad*)(b.base + plane * (b.z0 - b.hz_lo))}, stream_);
-        if (upper) pfor(q_hi, CopyQuads{(const Quad*)landing(region_, 3, par), (Quad*)(b.base + plane * b.z1)}, stream_);
     }
 #else
     (void)b;

@@ -173,6 +173,8 @@ Convolver::Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], in
         M_ = ax[0].T / 2;
     }
     for (int d = 0; d < 3; ++d) T_[d] = ax[d].T;
+    two_z_ = xmode != 1 && two_exchanges && (g.own_lo[2] != 0 || g.own_hi[2] != g.gdim[2]);
+    r2z_ = r2[2];
     ox_ = find_len_ops(M_);
     oy_ = find_len_ops(T_[1]);
     oz_ = find_len_ops(T_[2]);
@@ -345,8 +347,26 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
             mark(1); col(1, COL_FWD, nullptr, z0, z1);    // P2
         }
         mark(2); col(2, COL_CONV, k1hat);                 // P3
-        for (int z0 = 0; z0 < T_[2]; z0 += cp) {
-            const int z1 = std::min(T_[2], z0 + cp);
+        // Planes the quotient is computed on.  Exchange scheme 1 on a z-sharded box: the quotient of the halo planes on an interior
+        // side arrives (as its x-spectrum) from the z neighbour, so P4 / P5 skip them; planes beyond the reach of kernel2 are not
+        // read by anything that ends up in the responsibility box and are cleared (sane values for the transforms that follow).
+        // Sides that are volume faces keep all their planes: outside the volume the quotient is 1, and P5 writes exactly that.
+        int q0 = 0, q1 = T_[2];
+        if (two_z_ && mid_exchange_ && chunk_planes_ == 0) {
+            const size_t plane_bytes = sizeof(cpx) * (size_t)px_ * T_[1];
+            if (g_.own_lo[2] != 0) {
+                q0 = g_.own_lo[2] - t.org[2];
+                const int keep = std::min(q0, r2z_.lo);
+                if (q0 - keep > 0) dev::zero(work_, plane_bytes * (size_t)(q0 - keep), stream_);
+            }
+            if (g_.own_hi[2] != g_.gdim[2]) {
+                q1 = g_.own_hi[2] - t.org[2];
+                const int first = std::min(T_[2], q1 + r2z_.hi);
+                if (T_[2] - first > 0) dev::zero(work_ + (size_t)px_ * T_[1] * first, plane_bytes * (size_t)(T_[2] - first), stream_);
+            }
+        }
+        for (int z0 = q0; z0 < q1; z0 += cp) {
+            const int z1 = std::min(q1, z0 + cp);
             mark(3); col(1, COL_INV, nullptr, z0, z1);    // P4
             a.src = img;                                  // P5: quotient, 1 where there is no image data
             mark(4); xpass(X_RATIO, a, z0, z1);
@@ -366,8 +386,10 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
         a.max_intensity = max_intensity;
         a.part_sum = part_sum + (size_t)ti * xblocks_;
         a.part_max = part_max + (size_t)ti * xblocks_;
-        for (int z0 = 0; z0 < T_[2]; z0 += cp) {
-            const int z1 = std::min(T_[2], z0 + cp);
+        // the update only touches the planes of the responsibility box: the inverse y pass before it is not needed anywhere else
+        const int u0 = chunk_planes_ == 0 ? std::max(0, t.lo[2] - t.org[2]) : 0, u1 = chunk_planes_ == 0 ? std::min(T_[2], t.hi[2] - t.org[2]) : T_[2];
+        for (int z0 = u0; z0 < u1; z0 += cp) {
+            const int z1 = std::min(u1, z0 + cp);
             mark(7); col(1, COL_INV, nullptr, z0, z1);    // P8
             mark(8); xpass(X_UPDATE, a, z0, z1);
         }
@@ -657,8 +679,13 @@ void Engine::init_views() {
         throw Error("sharded context: the local arrays do not contain the halo rows (mvd_halo_rows)");
     for (View& vw : views_) { dev::free_(vw.k1hat); dev::free_(vw.k2hat); vw.k1hat = vw.k2hat = nullptr; }
     conv_.reset(new Convolver(cfg_.geom, r1, r2, 0, cfg_.max_len, stream_, tables_.get(), two));
-    if (two && (sharded(1) || sharded(2)) && conv_->num_tiles() != 1)
-        throw Error("exchange scheme 1 needs the local box to fit one FFT tile (use scheme 0 or more ranks)");
+    if (two && (sharded(1) || sharded(2))) {
+        // the quotient spectrum is exchanged tile by tile: tiles may follow each other along x (whole spectrum rows travel), but the
+        // box must fit one tile in y and z
+        for (const TileGeom& t : conv_->tiles())
+            if (t.org[1] != conv_->tiles()[0].org[1] || t.org[2] != conv_->tiles()[0].org[2])
+                throw Error("exchange scheme 1 needs the local box to fit one FFT tile in y and z (use scheme 0 or more ranks)");
+    }
     install_mid_exchange();
     for (View& vw : views_) {
         vw.k1hat = conv_->build_khat(vw.k1.data(), vw.k1d);

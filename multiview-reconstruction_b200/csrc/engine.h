@@ -100,6 +100,8 @@ class Convolver {
     void xpass(int kind, XArgs a, int z0 = 0, int z1 = -1);
     Geometry g_;
     int xmode_;
+    bool two_z_ = false;          // exchange scheme 1 on a z-sharded box: the quotient of the halo planes arrives from the z neighbours
+    Reach r2z_ = {0, 0};          // reach of kernel2 along z (planes the quotient exchange fills on either side of the own slab)
     int T_[3];     // real tile extents
     int M_;        // complex x length
     int px_;       // complex pitch

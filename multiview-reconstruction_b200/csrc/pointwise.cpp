@@ -182,11 +182,11 @@ void box_nonzero(stream_t s, const float* w, int nx, int ny, const int lo[3], co
     if (bx <= 0 || by <= 0 || bz <= 0) return;
     pfor((long long)bx * by * bz, BoxNonZero{w, nx, ny, lo[0], lo[1], lo[2], bx, by, flag_dev}, s);
 }
-struct FillParts {
+struct NeutralParts {
     double* ps; float* pm;
     MVD_HD void operator()(long long i) const { ps[i] = 0.0; pm[i] = -1.f; }
 };
-void clear_parts(stream_t s, double* part_sum, float* part_max, int n) { pfor(n, FillParts{part_sum, part_max}, s); }
+void clear_parts(stream_t s, double* part_sum, float* part_max, int n) { pfor(n, NeutralParts{part_sum, part_max}, s); }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // BlendingRealRandomAccess.computeWeight (M/process/fusion/transformed/weights/BlendingRealRandomAccess.java:95-130) for an

@@ -119,7 +119,7 @@ DIMS_CB = (40, 28, 24)
 KW_CB = dict(psf_size_xyz=(5, 5, 5), psf_sigma_xyz=(1.0, 1.1, 1.3), bead_density=512)
 
 
-def _worker_cb(rank, world, port, lib_path, out_dir, axis, scheme):
+def _worker_cb(rank, world, port, lib_path, out_dir, axis, scheme, dims=None, max_len=0):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch.distributed as dist
@@ -130,6 +130,7 @@ def _worker_cb(rank, world, port, lib_path, out_dir, axis, scheme):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lib = m.Lib(lib_path)
+    DIMS_CB = dims or globals()["DIMS_CB"]
     ds = o.make_synthetic(DIMS_CB, VIEWS, seed=6, **KW_CB)
     views, psi0, avg = o.make_oracle_views(ds, o.EFFICIENT_BAYESIAN)
     n = DIMS_CB[0] if axis == "z" else DIMS_CB[1]
@@ -141,7 +142,9 @@ def _worker_cb(rank, world, port, lib_path, out_dir, axis, scheme):
     loc = [m.DeconView(np.ascontiguousarray(ds.images[v][sl]), np.ascontiguousarray(ds.weights[v][sl]), ds.psfs[v],
                        m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(VIEWS)]
     kw = {"shard": (lo, hi, a0, a1 - a0)} if axis == "z" else {"shard_y": (lo, hi, a0, a1 - a0)}
-    dv = m.DeconViews(loc, global_dims_zyx=DIMS_CB, library=lib, exchange_scheme=scheme, **kw)
+    dv = m.DeconViews(loc, global_dims_zyx=DIMS_CB, library=lib, exchange_scheme=scheme, max_fft_len=max_len, **kw)
+    ntiles = dv.tile_info()["num_tiles"]
+    assert (ntiles > 1) == (max_len > 0)
     want = ((0 if rank == 0 else H), (0 if rank == world - 1 else H))
     assert (dv.halo_planes() if axis == "z" else dv.halo_rows()) == want
     py, pz = (1, world) if axis == "z" else (world, 1)
@@ -159,7 +162,7 @@ def _worker_cb(rank, world, port, lib_path, out_dir, axis, scheme):
             dv.enqueue_view_update(0)
     dv.set_exchange_callback(cb)
     dec.runIterations()                                         # the library calls back for every exchange: no host-side loop
-    assert calls == ([0] * 4 if scheme == 0 else [1, 0] * 4)
+    assert calls == ([0] * 4 if scheme == 0 else ([1] * ntiles + [0]) * 4)       # scheme 1: the quotient spectrum of every x tile, then psi
     own = (slice(lo - a0, hi - a0),) if axis == "z" else (slice(None), slice(lo - a0, hi - a0))
     np.save(os.path.join(out_dir, f"part{rank}.npy"), dec.getPSI()[own])
     dv.close()
@@ -178,6 +181,22 @@ def test_exchange_callback_and_two_exchange_scheme(hostemu_lib, oracle, tmp_path
     views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN)
     ref, _ = oracle.run_iterations_seq(psi0, views, 2, 0.0, dtype=np.float64)
     got = np.concatenate([np.load(tmp_path / f"part{r}.npy") for r in range(world)], axis=0 if axis == "z" else 1)
+    assert got.shape == ref.shape
+    assert oracle.rel_l2(got, ref) < 4e-6
+
+
+def test_two_exchange_scheme_with_several_x_tiles(hostemu_lib, oracle, tmp_path):
+    """exchange scheme 1 on a box that needs two FFT tiles along x (c4: 2048 + margins > one 2160-sample tile at equal cost): every tile
+    exchanges its own quotient spectrum; y / z still fit one tile."""
+    import torch.multiprocessing as mp
+    world, dims = 2, (40, 28, 100)
+    port = 31900 + (os.getpid() % 2000)
+    mp.start_processes(_worker_cb, args=(world, port, hostemu_lib.path, str(tmp_path), "z", 1, dims, 32), nprocs=world, join=True,
+                       start_method="spawn")
+    ds = oracle.make_synthetic(dims, VIEWS, seed=6, **KW_CB)
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN)
+    ref, _ = oracle.run_iterations_seq(psi0, views, 2, 0.0, dtype=np.float64)
+    got = np.concatenate([np.load(tmp_path / f"part{r}.npy") for r in range(world)], axis=0)
     assert got.shape == ref.shape
     assert oracle.rel_l2(got, ref) < 4e-6
 
