@@ -451,7 +451,10 @@ def run_ours(args):
     dv.pass_times(reset=True)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()                 # NVML initialisation takes 10 - 100 ms on this rank only ...
+    if world > 1:
+        dist.barrier()                  # ... so the ranks meet again AFTER it: the timed region starts on all ranks together
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -462,8 +465,13 @@ def run_ours(args):
     e1.synchronize()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    aux_ms, aux_n = dv.aux_times(reset=False)
     pass_ms, pass_n = dv.pass_times(reset=True)
+    dv.aux_times(reset=True)
     dv.set_profiling(False)
+    nvu = max(V * args.steps, 1)
+    aux = {"quotient_exchange_ms_per_view_update": round(aux_ms[0] / nvu, 4), "between_view_updates_ms_per_view_update": round(aux_ms[1] / nvu, 4),
+           "joins_and_clears_ms_per_view_update": round(aux_ms[2] / nvu, 4)}
     rank_pass_ms = None
     if world > 1:
         t = torch.tensor([ms], device=f"cuda:{local}")
@@ -532,7 +540,7 @@ def run_ours(args):
         if rank == 0:
             print(json.dumps({"metric": "voxel*view*iterations/s", "value": value, "n_gpus": world, "ms_per_step": ms / args.steps,
                               "note": "profiling run (--skip-e2e): not a bench line", "transport": transport, "parity": parity,
-                              "fft_tile_xyz": info["tile_dims_xyz"], "tiles_per_gpu": info["num_tiles"], "pass_ms_per_step_by_rank": rank_pass_ms,
+                              "fft_tile_xyz": info["tile_dims_xyz"], "tiles_per_gpu": info["num_tiles"], "pass_ms_per_step_by_rank": rank_pass_ms, "aux_rank0": aux,
                               "all_passes_ms_per_launch": [round(a / max(b, 1), 4) for a, b in zip(pass_ms, pass_n)]}))
         if comm is not None:
             comm.close()
@@ -616,6 +624,7 @@ def run_ours(args):
         }
         if rank_pass_ms is not None:
             line["pass_ms_per_step_by_rank"] = rank_pass_ms      # the step minus this = halo exchange + waiting for the slowest neighbour
+            line["aux_rank0"] = aux
         print(json.dumps(line), flush=True)
     if comm is not None:
         comm.close()

@@ -277,6 +277,10 @@ MVD_API int mvd_set_reduce_callback(mvd_context* ctx, mvd_reduce_fn fn, void* us
  * view update.  ms[] are accumulated milliseconds, counts[] the number of launches; reset != 0 clears them.   */
 MVD_API int mvd_set_profiling(mvd_context* ctx, int on);
 MVD_API int mvd_get_pass_times(mvd_context* ctx, double ms[9], long long counts[9], int reset);
+/* The rest of a view update as the compute stream sees it: [0] the quotient exchange of scheme 1 (from its start to the next pass),
+ * [1] from the end of P9 to the first pass of the next view update (statistics kernels, psi exchange, launch gaps), [2] everything else
+ * between passes (joining a travelling exchange, clearing rows / planes nobody delivers).                                             */
+MVD_API int mvd_get_aux_times(mvd_context* ctx, double ms[3], long long counts[3], int reset);
 
 /* Generic FFT convolution of a host volume with a host kernel on the device (used by the PSF derivation; exported for
  * tests and callers that need U/FFTConvolution.convolve semantics, U/FFTConvolution.java:490-603): out has the size of img,

@@ -118,6 +118,7 @@ SYMBOLS = {
     "mvd_enqueue_view_update": (C.c_int, [C.c_void_p, C.c_int]),
     "mvd_synchronize": (C.c_int, [C.c_void_p]),
     "mvd_fetch_stats": (C.c_int, [C.c_void_p, C.c_int, _D]),
+    "mvd_get_aux_times": (C.c_int, [C.c_void_p, _D, C.POINTER(C.c_longlong), C.c_int]),
     "mvd_tile_info": (C.c_int, [C.c_void_p, _I, _I, _D, _I]),
     "mvd_halo_planes": (C.c_int, [C.c_void_p, _I, _I]),
     "mvd_halo_rows": (C.c_int, [C.c_void_p, _I, _I]),
@@ -545,6 +546,13 @@ class DeconViews:
         ms = (C.c_double * 9)()
         n = (C.c_longlong * 9)()
         self.lib.check(self.lib.dll.mvd_get_pass_times(self._ctx, ms, n, 1 if reset else 0))
+        return [float(x) for x in ms], [int(x) for x in n]
+
+    def aux_times(self, reset: bool = True):
+        """accumulated milliseconds / counts of [quotient exchange, end of P9 .. next view update, other gaps] as the compute stream sees them"""
+        ms = (C.c_double * 3)()
+        n = (C.c_longlong * 3)()
+        self.lib.check(self.lib.dll.mvd_get_aux_times(self._ctx, ms, n, 1 if reset else 0))
         return [float(x) for x in ms], [int(x) for x in n]
 
     # ---- weight masks on the device (BlendingRealRandomAccess + NormalizingRandomAccess) --------------------------------

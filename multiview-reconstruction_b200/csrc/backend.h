@@ -54,6 +54,17 @@ inline void d2d(void* d, const void* s_, size_t n, stream_t s) { MVD_CUDA_CHECK(
 inline void zero(void* d, size_t n, stream_t s) { MVD_CUDA_CHECK(cudaMemsetAsync(d, 0, n, s)); }
 inline void sync(stream_t s) { MVD_CUDA_CHECK(cudaStreamSynchronize(s)); }
 inline stream_t stream_create() { cudaStream_t s; MVD_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return s; }
+inline stream_t stream_create_high_priority() {
+    int lo = 0, hi = 0;
+    MVD_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    cudaStream_t s;
+    MVD_CUDA_CHECK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
+    return s;
+}
+// clears `height` runs of `width` bytes that start `pitch` bytes apart
+inline void zero2d(void* d, size_t pitch, size_t width, size_t height, stream_t s) {
+    if (width && height) MVD_CUDA_CHECK(cudaMemset2DAsync(d, pitch, 0, width, height, s));
+}
 inline void stream_destroy(stream_t s) { if (s) cudaStreamDestroy(s); }
 typedef cudaEvent_t event_t;
 inline event_t event_create() { cudaEvent_t e; MVD_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); return e; }
@@ -98,6 +109,10 @@ inline void d2d(void* d, const void* s_, size_t n, stream_t) { std::memmove(d, s
 inline void zero(void* d, size_t n, stream_t) { std::memset(d, 0, n); }
 inline void sync(stream_t) {}
 inline stream_t stream_create() { return nullptr; }
+inline stream_t stream_create_high_priority() { return nullptr; }
+inline void zero2d(void* d, size_t pitch, size_t width, size_t height, stream_t) {
+    for (size_t i = 0; i < height; ++i) std::memset((char*)d + i * pitch, 0, width);
+}
 inline void stream_destroy(stream_t) {}
 typedef void* event_t;
 inline event_t event_create() { return nullptr; }

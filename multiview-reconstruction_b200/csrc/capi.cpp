@@ -390,6 +390,13 @@ int mvd_get_pass_times(mvd_context* ctx, double ms[9], long long counts[9], int 
     });
 }
 
+int mvd_get_aux_times(mvd_context* ctx, double ms[3], long long counts[3], int reset) {
+    return guarded([&] {
+        require(ctx && ms && counts && ctx->engine->convolver(), "bad argument");
+        ctx->engine->convolver()->collect_aux_times(ms, counts, reset != 0);
+    });
+}
+
 int mvd_convolve(int device, const float* img, const int dims[3], const float* kernel, const int kdims[3], int ext,
                  float ext_value, float* out) {
     return guarded([&] {

@@ -146,10 +146,11 @@ static void check_box(const HaloBox& b, bool ylower, bool yupper, bool zlower, b
         throw Error("halo exchange: the array does not contain the halo planes");
 }
 
-void HaloComm::exchange(const HaloBox& b, bool force_nccl) {
+void HaloComm::exchange(const HaloBox& b, bool force_nccl, stream_t s) {
+    if (!s) s = stream_;
     const bool ydo = py_ > 1 && (b.hy_lo > 0 || b.hy_hi > 0), zdo = pz_ > 1 && (b.hz_lo > 0 || b.hz_hi > 0);
     check_box(b, ydo && ry_ > 0, ydo && ry_ < py_ - 1, zdo && rz_ > 0, zdo && rz_ < pz_ - 1);
-    if (peer_ && !force_nccl) exchange_peer(b); else exchange_nccl(b);
+    if (peer_ && !force_nccl) exchange_peer(b, s); else exchange_nccl(b, s);
 }
 
 void HaloComm::all_reduce(double* host_values, int count, int op) {
@@ -174,7 +175,7 @@ void HaloComm::all_reduce(double* host_values, int count, int op) {
 
 // Neighbour below (ry-1 / rz-1): it needs my first h*_hi own rows / planes (its upper halo) and sends its last h*_lo ones (my lower
 // halo); the neighbour above mirrors that.  The widths are the same on every rank (they come from the kernel extents).
-void HaloComm::exchange_nccl(const HaloBox& b) {
+void HaloComm::exchange_nccl(const HaloBox& b, stream_t xs) {
 #ifndef MVD_HOST_EMU
     NcclApi& n = nccl();
     ncclComm_t c = (ncclComm_t)comm_->raw();
@@ -183,22 +184,22 @@ void HaloComm::exchange_nccl(const HaloBox& b) {
         const size_t per_row = (size_t)b.row_floats * (size_t)(b.z1 - b.z0);
         reserve((size_t)std::max(b.hy_lo, b.hy_hi) * per_row);
         const size_t cnt_lo = (size_t)b.hy_lo * per_row, cnt_hi = (size_t)b.hy_hi * per_row;
-        if (lower) pack_rows(b, stage_[0], b.y0, b.hy_hi, 1, stream_);
-        if (upper) pack_rows(b, stage_[1], b.y1 - b.hy_lo, b.hy_lo, 1, stream_);
+        if (lower) pack_rows(b, stage_[0], b.y0, b.hy_hi, 1, xs);
+        if (upper) pack_rows(b, stage_[1], b.y1 - b.hy_lo, b.hy_lo, 1, xs);
         nccl_check(n.GroupStart(), "group");
         if (lower) {
             const int peer = (ry_ - 1) * pz_ + rz_;
-            if (cnt_hi) nccl_check(n.Send(stage_[0], cnt_hi, kNcclFloat, peer, c, stream_), "send");
-            if (cnt_lo) nccl_check(n.Recv(stage_[2], cnt_lo, kNcclFloat, peer, c, stream_), "recv");
+            if (cnt_hi) nccl_check(n.Send(stage_[0], cnt_hi, kNcclFloat, peer, c, xs), "send");
+            if (cnt_lo) nccl_check(n.Recv(stage_[2], cnt_lo, kNcclFloat, peer, c, xs), "recv");
         }
         if (upper) {
             const int peer = (ry_ + 1) * pz_ + rz_;
-            if (cnt_lo) nccl_check(n.Send(stage_[1], cnt_lo, kNcclFloat, peer, c, stream_), "send");
-            if (cnt_hi) nccl_check(n.Recv(stage_[3], cnt_hi, kNcclFloat, peer, c, stream_), "recv");
+            if (cnt_lo) nccl_check(n.Send(stage_[1], cnt_lo, kNcclFloat, peer, c, xs), "send");
+            if (cnt_hi) nccl_check(n.Recv(stage_[3], cnt_hi, kNcclFloat, peer, c, xs), "recv");
         }
         nccl_check(n.GroupEnd(), "group");
-        if (lower) pack_rows(b, stage_[2], b.y0 - b.hy_lo, b.hy_lo, 0, stream_);
-        if (upper) pack_rows(b, stage_[3], b.y1, b.hy_hi, 0, stream_);
+        if (lower) pack_rows(b, stage_[2], b.y0 - b.hy_lo, b.hy_lo, 0, xs);
+        if (upper) pack_rows(b, stage_[3], b.y1, b.hy_hi, 0, xs);
     }
     if (pz_ > 1 && (b.hz_lo > 0 || b.hz_hi > 0)) {
         const bool lower = rz_ > 0, upper = rz_ < pz_ - 1;
@@ -207,18 +208,18 @@ void HaloComm::exchange_nccl(const HaloBox& b) {
         nccl_check(n.GroupStart(), "group");
         if (lower) {
             const int peer = ry_ * pz_ + rz_ - 1;
-            if (cnt_hi) nccl_check(n.Send(b.base + plane * b.z0, cnt_hi, kNcclFloat, peer, c, stream_), "send");
-            if (cnt_lo) nccl_check(n.Recv(b.base + plane * (b.z0 - b.hz_lo), cnt_lo, kNcclFloat, peer, c, stream_), "recv");
+            if (cnt_hi) nccl_check(n.Send(b.base + plane * b.z0, cnt_hi, kNcclFloat, peer, c, xs), "send");
+            if (cnt_lo) nccl_check(n.Recv(b.base + plane * (b.z0 - b.hz_lo), cnt_lo, kNcclFloat, peer, c, xs), "recv");
         }
         if (upper) {
             const int peer = ry_ * pz_ + rz_ + 1;
-            if (cnt_lo) nccl_check(n.Send(b.base + plane * (b.z1 - b.hz_lo), cnt_lo, kNcclFloat, peer, c, stream_), "send");
-            if (cnt_hi) nccl_check(n.Recv(b.base + plane * b.z1, cnt_hi, kNcclFloat, peer, c, stream_), "recv");
+            if (cnt_lo) nccl_check(n.Send(b.base + plane * (b.z1 - b.hz_lo), cnt_lo, kNcclFloat, peer, c, xs), "send");
+            if (cnt_hi) nccl_check(n.Recv(b.base + plane * b.z1, cnt_hi, kNcclFloat, peer, c, xs), "recv");
         }
         nccl_check(n.GroupEnd(), "group");
     }
 #else
-    (void)b;
+    (void)b; (void)xs;
 #endif
 }
 
@@ -335,9 +336,9 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(HaloSeg s0, HaloSeg s1, 
         else { const long long k = i - s0.count; s1.vol[s1.vol_index(k)] = s1.stage[k]; }
     }
 }
-inline int halo_grid(long long n) {
+inline int halo_grid(long long n, int per_sm = 8) {
     long long blocks = (n + 255) / 256;
-    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    if (blocks > 148LL * per_sm) blocks = 148LL * per_sm;
     return (int)(blocks < 1 ? 1 : blocks);
 }
 struct PeerInfo {
@@ -431,7 +432,7 @@ void HaloComm::close_peer() {
 #endif
 }
 
-void HaloComm::exchange_peer(const HaloBox& b) {
+void HaloComm::exchange_peer(const HaloBox& b, stream_t xs) {
 #ifndef MVD_HOST_EMU
     ++seq_;
     const int par = (int)(seq_ & 1u);
@@ -448,18 +449,18 @@ void HaloComm::exchange_peer(const HaloBox& b) {
         if (quads && (lower || upper)) {
             HaloSeg p0 = make_seg(b, lower ? landing(nb_region_[0], 1, par) : nullptr, b.y0, lower ? b.hy_hi : 0, b.z0, planes);
             HaloSeg p1 = make_seg(b, upper ? landing(nb_region_[1], 0, par) : nullptr, b.y1 - b.hy_lo, upper ? b.hy_lo : 0, b.z0, planes);
-            halo_push_kernel<<<halo_grid(p0.count + p1.count), 256, 0, stream_>>>(p0, p1, lower ? flags(nb_region_[0]) + 1 : nullptr,
+            halo_push_kernel<<<halo_grid(p0.count + p1.count, 4), 256, 0, xs>>>(p0, p1, lower ? flags(nb_region_[0]) + 1 : nullptr,
                                                                                    upper ? flags(nb_region_[1]) + 0 : nullptr, seq_, done);
             HaloSeg u0 = make_seg(b, lower ? landing(region_, 0, par) : nullptr, b.y0 - b.hy_lo, lower ? b.hy_lo : 0, b.z0, planes);
             HaloSeg u1 = make_seg(b, upper ? landing(region_, 1, par) : nullptr, b.y1, upper ? b.hy_hi : 0, b.z0, planes);
-            halo_pull_kernel<<<halo_grid(u0.count + u1.count), 256, 0, stream_>>>(u0, u1, lower ? mine + 0 : nullptr, upper ? mine + 1 : nullptr, seq_, tmo);
+            halo_pull_kernel<<<halo_grid(u0.count + u1.count, 2), 256, 0, xs>>>(u0, u1, lower ? mine + 0 : nullptr, upper ? mine + 1 : nullptr, seq_, tmo);
             MVD_CUDA_CHECK(cudaGetLastError());
         } else {
-            if (lower) { pack_rows(b, landing(nb_region_[0], 1, par), b.y0, b.hy_hi, 1, stream_); pfor(1, SignalArrival{flags(nb_region_[0]) + 1, seq_}, stream_); }
-            if (upper) { pack_rows(b, landing(nb_region_[1], 0, par), b.y1 - b.hy_lo, b.hy_lo, 1, stream_); pfor(1, SignalArrival{flags(nb_region_[1]) + 0, seq_}, stream_); }
-            if (lower || upper) pfor(1, AwaitArrival{lower ? mine + 0 : nullptr, upper ? mine + 1 : nullptr, seq_}, stream_);
-            if (lower) pack_rows(b, landing(region_, 0, par), b.y0 - b.hy_lo, b.hy_lo, 0, stream_);
-            if (upper) pack_rows(b, landing(region_, 1, par), b.y1, b.hy_hi, 0, stream_);
+            if (lower) { pack_rows(b, landing(nb_region_[0], 1, par), b.y0, b.hy_hi, 1, xs); pfor(1, SignalArrival{flags(nb_region_[0]) + 1, seq_}, xs); }
+            if (upper) { pack_rows(b, landing(nb_region_[1], 0, par), b.y1 - b.hy_lo, b.hy_lo, 1, xs); pfor(1, SignalArrival{flags(nb_region_[1]) + 0, seq_}, xs); }
+            if (lower || upper) pfor(1, AwaitArrival{lower ? mine + 0 : nullptr, upper ? mine + 1 : nullptr, seq_}, xs);
+            if (lower) pack_rows(b, landing(region_, 0, par), b.y0 - b.hy_lo, b.hy_lo, 0, xs);
+            if (upper) pack_rows(b, landing(region_, 1, par), b.y1, b.hy_hi, 0, xs);
         }
     }
     if (pz_ > 1 && (b.hz_lo > 0 || b.hz_hi > 0)) {
@@ -469,24 +470,24 @@ void HaloComm::exchange_peer(const HaloBox& b) {
         if (quads && (lower || upper)) {                   // whole planes including the fresh y halos: all rows
             HaloSeg p0 = make_seg(b, lower ? landing(nb_region_[2], 3, par) : nullptr, 0, b.nrows, b.z0, lower ? b.hz_hi : 0);
             HaloSeg p1 = make_seg(b, upper ? landing(nb_region_[3], 2, par) : nullptr, 0, b.nrows, b.z1 - b.hz_lo, upper ? b.hz_lo : 0);
-            halo_push_kernel<<<halo_grid(p0.count + p1.count), 256, 0, stream_>>>(p0, p1, lower ? flags(nb_region_[2]) + 3 : nullptr,
+            halo_push_kernel<<<halo_grid(p0.count + p1.count, 4), 256, 0, xs>>>(p0, p1, lower ? flags(nb_region_[2]) + 3 : nullptr,
                                                                                    upper ? flags(nb_region_[3]) + 2 : nullptr, seq_, done);
             HaloSeg u0 = make_seg(b, lower ? landing(region_, 2, par) : nullptr, 0, b.nrows, b.z0 - b.hz_lo, lower ? b.hz_lo : 0);
             HaloSeg u1 = make_seg(b, upper ? landing(region_, 3, par) : nullptr, 0, b.nrows, b.z1, upper ? b.hz_hi : 0);
-            halo_pull_kernel<<<halo_grid(u0.count + u1.count), 256, 0, stream_>>>(u0, u1, lower ? mine + 2 : nullptr, upper ? mine + 3 : nullptr, seq_, tmo);
+            halo_pull_kernel<<<halo_grid(u0.count + u1.count, 2), 256, 0, xs>>>(u0, u1, lower ? mine + 2 : nullptr, upper ? mine + 3 : nullptr, seq_, tmo);
             MVD_CUDA_CHECK(cudaGetLastError());
         } else {
             // scalar path for boxes whose rows are not 16-byte granules (arbitrary bounding boxes): whole planes as dense rows
             const HaloBox pb = b;
-            if (lower) { pack_planes(pb, landing(nb_region_[2], 3, par), b.z0, b.hz_hi, 1, stream_); pfor(1, SignalArrival{flags(nb_region_[2]) + 3, seq_}, stream_); }
-            if (upper) { pack_planes(pb, landing(nb_region_[3], 2, par), b.z1 - b.hz_lo, b.hz_lo, 1, stream_); pfor(1, SignalArrival{flags(nb_region_[3]) + 2, seq_}, stream_); }
-            if (lower || upper) pfor(1, AwaitArrival{lower ? mine + 2 : nullptr, upper ? mine + 3 : nullptr, seq_}, stream_);
-            if (lower) pack_planes(pb, landing(region_, 2, par), b.z0 - b.hz_lo, b.hz_lo, 0, stream_);
-            if (upper) pack_planes(pb, landing(region_, 3, par), b.z1, b.hz_hi, 0, stream_);
+            if (lower) { pack_planes(pb, landing(nb_region_[2], 3, par), b.z0, b.hz_hi, 1, xs); pfor(1, SignalArrival{flags(nb_region_[2]) + 3, seq_}, xs); }
+            if (upper) { pack_planes(pb, landing(nb_region_[3], 2, par), b.z1 - b.hz_lo, b.hz_lo, 1, xs); pfor(1, SignalArrival{flags(nb_region_[3]) + 2, seq_}, xs); }
+            if (lower || upper) pfor(1, AwaitArrival{lower ? mine + 2 : nullptr, upper ? mine + 3 : nullptr, seq_}, xs);
+            if (lower) pack_planes(pb, landing(region_, 2, par), b.z0 - b.hz_lo, b.hz_lo, 0, xs);
+            if (upper) pack_planes(pb, landing(region_, 3, par), b.z1, b.hz_hi, 0, xs);
         }
     }
 #else
-    (void)b;
+    (void)b; (void)xs;
 #endif
 }
 

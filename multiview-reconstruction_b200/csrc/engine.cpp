@@ -175,6 +175,8 @@ Convolver::Convolver(const Geometry& g, const Reach r1[3], const Reach r2[3], in
     for (int d = 0; d < 3; ++d) T_[d] = ax[d].T;
     two_z_ = xmode != 1 && two_exchanges && (g.own_lo[2] != 0 || g.own_hi[2] != g.gdim[2]);
     r2z_ = r2[2];
+    r2y_ = r2[1];
+    for (int d = 0; d < 3; ++d) { shard_lo_[d] = g.own_lo[d] != 0; shard_hi_[d] = g.own_hi[d] != g.gdim[d]; }
     ox_ = find_len_ops(M_);
     oy_ = find_len_ops(T_[1]);
     oz_ = find_len_ops(T_[2]);
@@ -323,7 +325,7 @@ void Convolver::conv(const float* src, float* dst, const cpx* khat, int ext, flo
 
 void Convolver::view_update(const float* psi_in, float* psi_out, const float* img, const float* weight, const cpx* k1hat,
                             const cpx* k2hat, float lambda, float min_value, float max_intensity, double* part_sum, float* part_max,
-                            const unsigned char* skip) {
+                            const unsigned char* skip, const std::function<void()>* psi_join) {
     if (xmode_ != 0) throw Error("internal: view updates need the real-packed x mode");
     int ti = 0;
     const int cp = chunk_planes_ > 0 ? chunk_planes_ : T_[2];
@@ -339,12 +341,31 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
         XArgs a = base_xargs(t);
         // x/y pass chains run plane chunk by plane chunk so that the hand-over P1->P2, P4->P5->P6, P8->P9 stays in the 126 MB L2;
         // the z passes (P3, P7) need every plane and run over the whole tile.
-        for (int z0 = 0; z0 < T_[2]; z0 += cp) {
-            const int z1 = std::min(T_[2], z0 + cp);
-            a.src = psi_in;                               // P1: mirror-single outside the volume (MultiViewDeconvolutionSeq.java:115)
-            a.ext = EXT_MIRROR;
-            mark(0); xpass(X_FWD, a, z0, z1);
-            mark(1); col(1, COL_FWD, nullptr, z0, z1);    // P2
+        // own box of this rank in tile coordinates
+        const int oy0 = std::max(0, g_.own_lo[1] - t.org[1]), oy1 = std::min(T_[1], g_.own_hi[1] - t.org[1]);
+        const int oz0 = std::max(0, g_.own_lo[2] - t.org[2]), oz1 = std::min(T_[2], g_.own_hi[2] - t.org[2]);
+        a.src = psi_in;                                   // P1: mirror-single outside the volume (MultiViewDeconvolutionSeq.java:115)
+        a.ext = EXT_MIRROR;
+        if (psi_join && *psi_join && chunk_planes_ == 0 && !std::getenv("MVD_DBG_NOP1SPLIT")) {
+            // the halo exchange of psi is still travelling: the lines of the own box do not read halo data (a reflected row at a
+            // volume face is an own row) and are transformed first; everything else follows once the halos are in place
+            a.fin[0] = oy0; a.fin[1] = oy1; a.fin[2] = oz0; a.fin[3] = oz1;
+            mark(0); xpass(X_FWD, a, oz0, oz1);
+            mark(11);
+            (*psi_join)();
+            psi_join = nullptr;
+            a.fin[0] = a.fin[1] = 0;
+            a.fout[0] = oy0; a.fout[1] = oy1; a.fout[2] = oz0; a.fout[3] = oz1;
+            mark(0); xpass(X_FWD, a);
+            a.fout[0] = a.fout[1] = 0;
+            mark(1); col(1, COL_FWD, nullptr);            // P2
+        } else {
+            if (psi_join && *psi_join) { (*psi_join)(); psi_join = nullptr; }
+            for (int z0 = 0; z0 < T_[2]; z0 += cp) {
+                const int z1 = std::min(T_[2], z0 + cp);
+                mark(0); xpass(X_FWD, a, z0, z1);
+                mark(1); col(1, COL_FWD, nullptr, z0, z1);    // P2
+            }
         }
         mark(2); col(2, COL_CONV, k1hat);                 // P3
         // Planes the quotient is computed on.  Exchange scheme 1 on a z-sharded box: the quotient of the halo planes on an interior
@@ -365,17 +386,55 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
                 if (T_[2] - first > 0) dev::zero(work_ + (size_t)px_ * T_[1] * first, plane_bytes * (size_t)(T_[2] - first), stream_);
             }
         }
-        for (int z0 = q0; z0 < q1; z0 += cp) {
-            const int z1 = std::min(q1, z0 + cp);
-            mark(3); col(1, COL_INV, nullptr, z0, z1);    // P4
+        if (mid_exchange_ && mid_join_ && chunk_planes_ == 0 && !std::getenv("MVD_DBG_NOP5SPLIT")) {
+            // Boundary-first quotient pass.  This rank computes the quotient on its own box, extended to the tile edge where the box
+            // ends at a volume face (outside the volume the quotient is 1, and P5 writes exactly that); the neighbours deliver the
+            // rest within the reach of kernel2, what lies beyond is cleared.  The lines the neighbours are waiting for -- own lines
+            // within that reach of an interior side -- run first, then the exchange starts and travels while the deep interior
+            // follows.
+            const int ey0 = shard_lo_[1] ? oy0 : 0, ey1 = shard_hi_[1] ? oy1 : T_[1];
+            mark(3); col(1, COL_INV, nullptr, q0, q1);    // P4 (own planes; face sides keep theirs)
+            mark(11);
+            const size_t row_bytes = sizeof(cpx) * (size_t)px_, plane_bytes = row_bytes * (size_t)T_[1];
+            if (shard_lo_[1] && ey0 - r2y_.lo > 0)
+                dev::zero2d(work_ + (size_t)px_ * T_[1] * q0, plane_bytes, row_bytes * (size_t)(ey0 - r2y_.lo), (size_t)(q1 - q0), stream_);
+            if (shard_hi_[1] && ey1 + r2y_.hi < T_[1])
+                dev::zero2d(work_ + (size_t)px_ * ((size_t)T_[1] * q0 + (size_t)(ey1 + r2y_.hi)), plane_bytes,
+                            row_bytes * (size_t)(T_[1] - ey1 - r2y_.hi), (size_t)(q1 - q0), stream_);
+            // deep interior: further than the neighbours' reach from every interior side
+            const int dy0 = ey0 + (shard_lo_[1] ? r2y_.hi : 0), dy1 = ey1 - (shard_hi_[1] ? r2y_.lo : 0);
+            const int dz0 = q0 + (shard_lo_[2] ? r2z_.hi : 0), dz1 = q1 - (shard_hi_[2] ? r2z_.lo : 0);
+            const bool deep = dy1 > dy0 && dz1 > dz0;
             a.src = img;                                  // P5: quotient, 1 where there is no image data
-            mark(4); xpass(X_RATIO, a, z0, z1);
-            if (!mid_exchange_) { mark(5); col(1, COL_FWD, nullptr, z0, z1); }   // P6
-        }
-        if (mid_exchange_) {                              // scheme B: the neighbours' quotient rows / planes arrive as x-spectra
-            mark(-1);
+            a.fin[0] = ey0; a.fin[1] = ey1; a.fin[2] = q0; a.fin[3] = q1;
+            a.fkeep = 1;      // + the lines outside the volume (margins at volume faces): their quotient is 1, nobody delivers them
+            if (deep) { a.fout[0] = dy0; a.fout[1] = dy1; a.fout[2] = dz0; a.fout[3] = dz1; }
+            mark(4); xpass(X_RATIO, a, q0, q1);
+            mark(9);
+            a.fkeep = 0;
             mid_exchange_(work_, t);
-            for (int z0 = 0; z0 < T_[2]; z0 += cp) { mark(5); col(1, COL_FWD, nullptr, z0, std::min(T_[2], z0 + cp)); }
+            if (deep) {
+                a.fout[0] = a.fout[1] = 0;
+                a.fin[0] = dy0; a.fin[1] = dy1; a.fin[2] = dz0; a.fin[3] = dz1;
+                mark(4); xpass(X_RATIO, a, dz0, dz1);
+                mark(9);
+            }
+            a.fin[0] = a.fin[1] = a.fout[0] = a.fout[1] = 0;
+            mid_join_();
+            mark(5); col(1, COL_FWD, nullptr);            // P6
+        } else {
+            for (int z0 = q0; z0 < q1; z0 += cp) {
+                const int z1 = std::min(q1, z0 + cp);
+                mark(3); col(1, COL_INV, nullptr, z0, z1);    // P4
+                a.src = img;                                  // P5: quotient, 1 where there is no image data
+                mark(4); xpass(X_RATIO, a, z0, z1);
+                if (!mid_exchange_) { mark(5); col(1, COL_FWD, nullptr, z0, z1); }   // P6
+            }
+            if (mid_exchange_) {                              // scheme B: the neighbours' quotient rows / planes arrive as x-spectra
+                mark(9);
+                mid_exchange_(work_, t);
+                for (int z0 = 0; z0 < T_[2]; z0 += cp) { mark(5); col(1, COL_FWD, nullptr, z0, std::min(T_[2], z0 + cp)); }
+            }
         }
         mark(6); col(2, COL_CONV, k2hat);                 // P7
         a.src = psi_in;                                   // P9
@@ -393,7 +452,7 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
             mark(7); col(1, COL_INV, nullptr, z0, z1);    // P8
             mark(8); xpass(X_UPDATE, a, z0, z1);
         }
-        mark(-1);
+        mark(10);
         ++ti;
     }
 }
@@ -490,6 +549,9 @@ Engine::~Engine() {
         dev::event_destroy(v.ready);
     }
     small_conv_.reset();
+    if (xstream_) { try { dev::sync(xstream_); } catch (...) {} }
+    dev::stream_destroy(xstream_);
+    dev::event_destroy(ev_compute_); dev::event_destroy(ev_psi_); dev::event_destroy(ev_mid_);
     dev::stream_destroy(copy_stream_);
     dev::free_(psi_[0]); dev::free_(psi_[1]);
     dev::free_(part_sum_); dev::free_(part_max_); dev::free_(stats_dev_);
@@ -710,11 +772,13 @@ void Engine::get_kernel(int v, int which, float* out) const {
 }
 
 void Engine::set_psi_host(const float* psi) {
+    join_halo();
     dev::set_device(cfg_.device);
     dev::h2d(psi_[cur_], psi, sizeof(float) * local_voxels(), stream_);
     dev::sync(stream_);
 }
 void Engine::get_psi_host(float* psi) {
+    join_halo();
     dev::set_device(cfg_.device);
     dev::d2h(psi, psi_[cur_], sizeof(float) * local_voxels(), stream_);
     dev::sync(stream_);
@@ -797,6 +861,7 @@ void Engine::psi_blur_sharded(const std::vector<float>& k3, int k) {
 }
 
 void Engine::psi_init(int type, double sigma, double* avg_out, float* max_out, bool set_img_to_avg) {
+    join_halo();
     dev::set_device(cfg_.device);
     const int V = cfg_.num_views;
     if (V > MVD_MAX_VIEWS) throw Error("too many views for the device PsiInit");
@@ -1006,6 +1071,7 @@ void Engine::get_weight_host(int v, float* out) {
 
 // MultiViewDeconvolutionMul.runNextIteration / ComputeBlockMulThreadCPU.runIteration (mul/ComputeBlockMulThreadCPU.java:87-188)
 void Engine::iteration_mul() {
+    join_halo();
     if (!inited_) throw Error("init_views() has not been called");
     dev::set_device(cfg_.device);
     const int V = cfg_.num_views;
@@ -1056,16 +1122,19 @@ void Engine::view_update(int v) {
         if (!skip_valid_) refresh_skip();
         skip = skip_.data() + (size_t)v * conv_->num_tiles();
     }
+    // a psi exchange that is still travelling is joined inside the update, after the lines that do not depend on it
+    const std::function<void()> join = [this] { join_halo(); };
     conv_->view_update(psi_[cur_], psi_[cur_ ^ 1], vw.img, vw.weight, vw.k1hat, vw.k2hat, cfg_.lambda, cfg_.min_value,
-                       vw.max_intensity, part_sum_, part_max_, skip);
+                       vw.max_intensity, part_sum_, part_max_, skip, halo_pending_ ? &join : nullptr);
+    join_halo();                                          // (every tile skipped: nothing joined it)
+    cur_ ^= 1;
+    if (has_exchange()) start_psi_exchange(psi_[cur_]);   // travels behind the statistics kernels and the next update's first lines
     // deterministic two-level reduction of the per-CTA partial statistics
     ReduceParts1 r1{part_sum_, part_max_, nparts, part_sum_ + nparts, part_max_ + nparts};
     pfor(256, r1, stream_);
     ReduceParts2 r2{part_sum_ + nparts, part_max_ + nparts, stats_dev_ + 2 * (size_t)stats_count_};
     pfor(1, r2, stream_);
     ++stats_count_;
-    cur_ ^= 1;
-    if (has_exchange()) exchange_psi(psi_[cur_]);
 }
 
 int Engine::skip_empty_tiles(bool on) {
@@ -1121,17 +1190,48 @@ void Engine::comm_attach(std::shared_ptr<NcclComm> comm, int py, int pz) {
     };
     account(psi_box(psi_[0]));
     if (cfg_.exchange_scheme == 1) account(spectrum_box(nullptr, conv_->tiles().at(0)));
+    join_halo();
     comm_.reset(new HaloComm(std::move(comm), py, pz, stream_, need_y, need_z));
+    // peer transport: the exchanges get their own high-priority stream and overlap the passes (MVD_OVERLAP=0: serialised on the compute stream)
+    const char* ov = std::getenv("MVD_OVERLAP");
+    overlap_ = comm_->transport() == 1 && !(ov && std::atoi(ov) == 0);
+    if (overlap_ && !xstream_) {
+        xstream_ = dev::stream_create_high_priority();
+        ev_compute_ = dev::event_create(); ev_psi_ = dev::event_create(); ev_mid_ = dev::event_create();
+    }
     install_mid_exchange();
 }
 
-void Engine::do_exchange(int which, const HaloBox& b, bool oversize) {
+void Engine::do_exchange(int which, const HaloBox& b, bool oversize, dev::event_t ev) {
     if (host_exchange_) {
         dev::sync(stream_);
         if (host_exchange_(host_exchange_user_, which, &b) != 0) throw Error("the host's exchange callback failed");
     } else if (comm_) {
-        comm_->exchange(b, oversize);
+        if (!overlap_) { comm_->exchange(b, oversize); return; }
+        // every exchange of an overlapping context runs on the exchange stream (they share landing buffers and sequence numbers, so
+        // they must stay ordered among themselves): it starts behind what the compute stream has enqueued so far ...
+        dev::event_record(ev_compute_, stream_);
+        dev::stream_wait(xstream_, ev_compute_);
+        comm_->exchange(b, oversize, xstream_);
+        // ... and the compute stream either continues and joins later (ev) or waits right away
+        dev::event_record(ev ? ev : ev_mid_, xstream_);
+        if (!ev) dev::stream_wait(stream_, ev_mid_);
     }
+}
+
+void Engine::start_psi_exchange(float* psi) {
+    if (host_exchange_) { pending_psi_ = psi; halo_pending_ = true; return; }     // deferred to the join
+    if (!comm_) return;
+    if (!overlap_) { do_exchange(0, psi_box(psi)); return; }
+    do_exchange(0, psi_box(psi), false, ev_psi_);
+    halo_pending_ = true;
+}
+
+void Engine::join_halo() {
+    if (!halo_pending_) return;
+    halo_pending_ = false;
+    if (host_exchange_) do_exchange(0, psi_box(pending_psi_));
+    else dev::stream_wait(stream_, ev_psi_);
 }
 
 // psi: scheme 0 ships what both convolutions read beyond the own box (r1 + r2), scheme 1 only the first convolution's reach
@@ -1165,16 +1265,21 @@ HaloBox Engine::spectrum_box(cpx* work, const TileGeom& t) const {
 void Engine::install_mid_exchange() {
     if (!conv_) return;
     if (cfg_.exchange_scheme != 1 || !(sharded(1) || sharded(2)) || !has_exchange()) { conv_->set_mid_exchange(nullptr); return; }
-    conv_->set_mid_exchange([this](cpx* work, const TileGeom& t) { do_exchange(1, spectrum_box(work, t)); });
+    // start + join: the quotient pass runs boundary first and the exchange travels behind its deep interior (host callback: the exchange
+    // is complete when start returns, the pass is split all the same)
+    conv_->set_mid_exchange([this](cpx* work, const TileGeom& t) { do_exchange(1, spectrum_box(work, t), false, overlap_ ? ev_mid_ : nullptr); },
+                            [this] { if (overlap_) dev::stream_wait(stream_, ev_mid_); });
 }
 
 void Engine::exchange_halos() {
+    join_halo();
     if (!has_exchange()) throw Error("no communicator attached (mvd_comm_attach / mvd_set_exchange_callback)");
     dev::set_device(cfg_.device);
     exchange_psi(psi_[cur_]);
 }
 
 void Engine::fetch_stats(int count, IterStats* out) {
+    join_halo();
     dev::set_device(cfg_.device);
     if (count > stats_count_) count = stats_count_;
     std::vector<double> h(2 * (size_t)std::max(count, 1));
@@ -1197,7 +1302,7 @@ void Engine::run_iterations(int n, IterStats* out) {
     for (int it = 0; it < n; ++it)
         for (int v = 0; v < cfg_.num_views; ++v) view_update(v);      // OSEM: psi updated after every view
     if (out) fetch_stats(n * cfg_.num_views, out);
-    else dev::sync(stream_);
+    else { join_halo(); dev::sync(stream_); }
 }
 
 void convolve_host(int device, stream_t stream_, Tables* tables, int max_len, const float* src, const int dims[3],
@@ -1254,7 +1359,7 @@ void Convolver::collect_pass_times(double ms[9], long long counts[9], bool reset
     dev::sync(stream_);
     for (size_t i = 0; i + 1 < prof_used_; ++i) {
         const int id = prof_ids_[i];
-        if (id < 0 || id > 8) continue;
+        if (id < 0 || id > 11) continue;
         float t = 0.f;
         MVD_CUDA_CHECK(cudaEventElapsedTime(&t, (cudaEvent_t)prof_events_[i], (cudaEvent_t)prof_events_[i + 1]));
         prof_ms_[id] += t;
@@ -1264,6 +1369,12 @@ void Convolver::collect_pass_times(double ms[9], long long counts[9], bool reset
 #endif
     for (int i = 0; i < 9; ++i) { ms[i] = prof_ms_[i]; counts[i] = prof_n_[i]; }
     if (reset) for (int i = 0; i < 9; ++i) { prof_ms_[i] = 0; prof_n_[i] = 0; }
+}
+void Convolver::collect_aux_times(double ms[3], long long counts[3], bool reset) {
+    double pm[9]; long long pn[9];
+    collect_pass_times(pm, pn, false);
+    for (int i = 0; i < 3; ++i) { ms[i] = prof_ms_[9 + i]; counts[i] = prof_n_[9 + i]; }
+    if (reset) for (int i = 9; i < 12; ++i) { prof_ms_[i] = 0; prof_n_[i] = 0; }
 }
 
 }  // namespace mvd

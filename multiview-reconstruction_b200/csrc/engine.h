@@ -63,7 +63,11 @@ class Convolver {
               bool two_exchanges = false);
     ~Convolver();
     // called between P5 and P6 of a view update with the tile's x-spectrum of the quotient ([Tz][Ty][px] complex)
-    void set_mid_exchange(std::function<void(cpx* work, const TileGeom& t)> f) { mid_exchange_ = std::move(f); }
+    // start: begins the exchange of the quotient's x-spectrum (may return before it completed); join: everything it delivers is in place
+    // for the work that follows on the compute stream.  Between the two the pass computes the lines the exchange does not touch.
+    void set_mid_exchange(std::function<void(cpx* work, const TileGeom& t)> start, std::function<void()> join = nullptr) {
+        mid_exchange_ = std::move(start); mid_join_ = std::move(join);
+    }
     int pitch() const { return px_; }
 
     size_t tile_elems() const { return (size_t)px_ * T_[1] * T_[2]; }            // complex elements per spectrum
@@ -87,12 +91,16 @@ class Convolver {
     // (a block without content, DeconView.filterBlocksForContent)
     void view_update(const float* psi_in, float* psi_out, const float* img, const float* weight, const cpx* k1hat,
                      const cpx* k2hat, float lambda, float min_value, float max_intensity, double* part_sum, float* part_max,
-                     const unsigned char* skip = nullptr);
+                     const unsigned char* skip = nullptr, const std::function<void()>* psi_join = nullptr);
     // conv1 -> quotient -> conv2 without the update: the "integral" of one view (P1..P8 + real store), used by the Mul iteration
     void integral(const float* psi_in, const float* img, const cpx* k1hat, const cpx* k2hat, float* integral_out);
     // per-pass CUDA-event timing (bench.py's roofline leg): P1..P9 -> slots 0..8
     void set_profiling(bool on) { prof_on_ = on; }
     void collect_pass_times(double ms[9], long long counts[9], bool reset);
+    // what is not a pass: [0] the quotient exchange as the compute stream sees it (start .. next pass), [1] from the end of P9 to the first
+    // pass of the next view update (statistics kernels, psi exchange or its start, launch gaps)
+    // [2] everything else between passes (joins of a travelling exchange, clearing of rows / planes)
+    void collect_aux_times(double ms[3], long long counts[3], bool reset);
 
   private:
     XArgs base_xargs(const TileGeom& t) const;
@@ -115,6 +123,9 @@ class Convolver {
     float* kdev_ = nullptr;     // kernel staging, grows on demand
     size_t kdev_cap_ = 0;
     std::function<void(cpx*, const TileGeom&)> mid_exchange_;
+    std::function<void()> mid_join_;
+    Reach r2y_ = {0, 0};
+    bool shard_lo_[3] = {false, false, false}, shard_hi_[3] = {false, false, false};   // this side of the box has a neighbour (not a volume face)
     // software L2 prefetch distance in CTAs for the x, y and z passes (MVD_PF_X / MVD_PF_Y / MVD_PF_Z override)
     int pf_x_ = 37, pf_y_ = 296, pf_z_ = 0;     // measured (c3, two-stage column plans): the z convolution is 15 % faster without
     int chunk_planes_ = 0;  // planes per L2-resident chunk of the x/y pass chains (0 = whole tile per launch)
@@ -124,8 +135,8 @@ class Convolver {
     std::vector<void*> prof_events_;
     std::vector<int> prof_ids_;
     size_t prof_used_ = 0;
-    double prof_ms_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long prof_n_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double prof_ms_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};      // 0..8: passes P1..P9; 9: quotient exchange; 10: between two view updates
+    long long prof_n_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 AxisTiling plan_axis(int gdim, int own_lo, int own_hi, Reach r1, Reach r2, bool is_x, int max_len, bool two_exchanges = false);
@@ -170,13 +181,14 @@ class HaloComm {
     ~HaloComm();
     // enqueued on the stream; the host does not block.  force_nccl: a one-off exchange larger than the landing buffers (PsiInit);
     // every rank must pass the same value
-    void exchange(const HaloBox& b, bool force_nccl = false);
+    // s: the stream the exchange is enqueued on (null = the context's compute stream)
+    void exchange(const HaloBox& b, bool force_nccl = false, stream_t s = nullptr);
     void all_reduce(double* host_values, int count, int op);      // collective, synchronises the stream; op 0 sum, 1 max
     int transport() const { return peer_ ? 1 : 0; }      // 0: NCCL send/recv, 1: direct stores into the neighbours' memory
   private:
     void reserve(size_t floats);
-    void exchange_nccl(const HaloBox& b);
-    void exchange_peer(const HaloBox& b);
+    void exchange_nccl(const HaloBox& b, stream_t s);
+    void exchange_peer(const HaloBox& b, stream_t s);
     void setup_peer(size_t need_y, size_t need_z);
     void close_peer();
     std::shared_ptr<NcclComm> comm_;
@@ -272,7 +284,7 @@ class Engine {
 
     void set_psi_host(const float* psi);
     void get_psi_host(float* psi);
-    float* psi_device() { return psi_[cur_]; }
+    float* psi_device() { join_halo(); return psi_[cur_]; }
     float* psi_next_device() { return psi_[cur_ ^ 1]; }
     void set_max_intensity(const float* mx) { for (int v = 0; v < cfg_.num_views; ++v) views_[v].max_intensity = mx[v]; }
     float max_intensity(int v) const { return views_[v].max_intensity; }
@@ -311,7 +323,7 @@ class Engine {
     int skip_empty_tiles(bool on);
     void fetch_stats(int count, IterStats* out);           // last `count` view updates (synchronises)
     void run_iterations(int n, IterStats* out /* n*V or null */);
-    void synchronize() { dev::sync(stream_); }
+    void synchronize() { join_halo(); dev::sync(stream_); }
     stream_t stream() const { return stream_; }
 
     Convolver* convolver() { return conv_.get(); }
@@ -369,7 +381,19 @@ class Engine {
     Reach r1_[3] = {{0, 0}, {0, 0}, {0, 0}}, r2_[3] = {{0, 0}, {0, 0}, {0, 0}};     // kernel reaches (max over views)
     bool sharded(int d) const { return cfg_.geom.own_lo[d] != 0 || cfg_.geom.own_hi[d] != cfg_.geom.gdim[d]; }
     bool has_exchange() const { return comm_ != nullptr || host_exchange_ != nullptr; }
-    void do_exchange(int which, const HaloBox& b, bool oversize = false);
+    // ev != null: asynchronous on the exchange stream, `ev` is recorded behind it (the caller joins); else complete on return of the
+    // compute stream's point of view
+    void do_exchange(int which, const HaloBox& b, bool oversize = false, dev::event_t ev = nullptr);
+    // The psi exchange that follows a view update is not waited for: it travels (on its own high-priority stream, or -- host callback --
+    // is simply deferred) while the next update transforms the lines that do not read halo data.  join_halo() makes the halos valid for
+    // whatever follows on the compute stream; every entry point that touches psi calls it.
+    void start_psi_exchange(float* psi);
+    void join_halo();
+    bool halo_pending_ = false;
+    float* pending_psi_ = nullptr;
+    bool overlap_ = false;                  // exchanges run on xstream_ (peer transport)
+    stream_t xstream_ = nullptr;
+    dev::event_t ev_compute_ = nullptr, ev_psi_ = nullptr, ev_mid_ = nullptr;
     void exchange_psi(float* psi);
     HaloBox psi_box(float* psi) const;
     HaloBox spectrum_box(cpx* work, const TileGeom& t) const;

@@ -111,14 +111,11 @@ __global__ void __launch_bounds__(P::XTHREADS, xp_min_blocks<P>()) x_kernel_p(co
     __syncthreads();
 
     auto has_work = [&](int bx) -> bool {              // CTA-uniform
-        if constexpr (KIND == X_UPDATE || KIND == X_INV) {
-            bool any = false;
-            const int l0 = a.line0 + bx * XL;
-            for (int i = 0; i < XL; ++i) any = any || x_line_in_box(a, l0 + i);
-            return any;
-        } else {
-            return true;
-        }
+        bool any = false;
+        const int l0 = a.line0 + bx * XL;
+        if constexpr (KIND == X_UPDATE || KIND == X_INV) { for (int i = 0; i < XL; ++i) any = any || x_line_in_box(a, l0 + i); }
+        else { for (int i = 0; i < XL; ++i) any = any || x_line_selected(a, l0 + i); }
+        return any;
     };
     auto issue_load = [&](int bx, cpx* dst, unsigned long long* bar) {   // one thread
         const int l0 = a.line0 + bx * XL;
@@ -155,7 +152,8 @@ __global__ void __launch_bounds__(P::XTHREADS, xp_min_blocks<P>()) x_kernel_p(co
             if (tid == 0) {
                 const int l0 = a.line0 + bx * XL;
                 const int n = (a.line_end - l0) < XL ? (a.line_end - l0) : XL;
-                for (int ln = 0; ln < n; ++ln) tma::store_bulk(a.cdata + (long long)(l0 + ln) * a.px, sm + ln * L::LS, LINE_BYTES);
+                for (int ln = 0; ln < n; ++ln)
+                    if (x_line_selected(a, l0 + ln)) tma::store_bulk(a.cdata + (long long)(l0 + ln) * a.px, sm + ln * L::LS, LINE_BYTES);
                 tma::commit_group();
             }
         }
@@ -227,11 +225,12 @@ __global__ void __launch_bounds__(32 * WPC, xw_min_blocks<P, WPC>()) x_kernel_w(
     const unsigned pf_bytes = (unsigned)((pf_x1 - pf_x0) * 4) & ~15u;
     const bool pf_rows = a.pf_dist > 0 && (a.vol[0] & 3) == 0 && ((reinterpret_cast<unsigned long long>(a.src) & 15ull) == 0) && pf_bytes > 0;
     // lines outside the responsibility box of the update / inverse pass are skipped (no load, no work)
+    const bool filtered = (KIND == X_UPDATE || KIND == X_INV) || a.fin[1] > a.fin[0] || a.fout[1] > a.fout[0];
     auto has_work = [&](int l) -> bool {
         if constexpr (KIND == X_UPDATE || KIND == X_INV) return x_line_in_box(a, a.line0 + l);
-        else return true;
+        else return x_line_selected(a, a.line0 + l);
     };
-    if constexpr (KIND == X_UPDATE || KIND == X_INV) {
+    if (filtered) {
         while (ln < nlines && !has_work(ln)) ln += stride;
     }
     if (HAS_IN && lane == 0 && ln < nlines) issue_load(ln, buf0, &bars[0]);
@@ -241,7 +240,7 @@ __global__ void __launch_bounds__(32 * WPC, xw_min_blocks<P, WPC>()) x_kernel_w(
         const int b = it & 1;
         cpx* const sm = b ? buf1 : buf0;
         int nl = ln + stride;
-        if constexpr (KIND == X_UPDATE || KIND == X_INV) {
+        if (filtered) {
             while (nl < nlines && !has_work(nl)) nl += stride;
         }
         // the pass stores into `sm` from its first phase on: the bulk store that last read this buffer (two lines ago) must be done
