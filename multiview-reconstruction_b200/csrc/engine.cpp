@@ -323,6 +323,25 @@ void Convolver::conv(const float* src, float* dst, const cpx* khat, int ext, flo
     }
 }
 
+// selection rectangles {y0, y1, z0, z1} of a filtered x launch (XArgs::rect): kernels that deal single lines enumerate them
+static void rects_clear(XArgs& a) { a.nrect = 0; a.rect_start[0] = 0; }
+static void rects_add(XArgs& a, int y0, int y1, int z0, int z1) {
+    if (y1 <= y0 || z1 <= z0 || a.nrect >= 8) return;
+    int* r = a.rect[a.nrect];
+    r[0] = y0; r[1] = y1; r[2] = z0; r[3] = z1;
+    a.rect_start[a.nrect + 1] = a.rect_start[a.nrect] + (y1 - y0) * (z1 - z0);
+    ++a.nrect;
+}
+// outer box minus inner box (inner clipped to outer) as up to four rectangles: the z slabs below / above, the y strips beside
+static void rects_add_difference(XArgs& a, const int o[4], const int in[4]) {
+    const int iy0 = std::max(o[0], in[0]), iy1 = std::min(o[1], in[1]), iz0 = std::max(o[2], in[2]), iz1 = std::min(o[3], in[3]);
+    if (iy1 <= iy0 || iz1 <= iz0) { rects_add(a, o[0], o[1], o[2], o[3]); return; }
+    rects_add(a, o[0], o[1], o[2], iz0);
+    rects_add(a, o[0], o[1], iz1, o[3]);
+    rects_add(a, o[0], iy0, iz0, iz1);
+    rects_add(a, iy1, o[1], iz0, iz1);
+}
+
 void Convolver::view_update(const float* psi_in, float* psi_out, const float* img, const float* weight, const cpx* k1hat,
                             const cpx* k2hat, float lambda, float min_value, float max_intensity, double* part_sum, float* part_max,
                             const unsigned char* skip, const std::function<void()>* psi_join) {
@@ -349,15 +368,19 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
         if (psi_join && *psi_join && chunk_planes_ == 0 && !std::getenv("MVD_DBG_NOP1SPLIT")) {
             // the halo exchange of psi is still travelling: the lines of the own box do not read halo data (a reflected row at a
             // volume face is an own row) and are transformed first; everything else follows once the halos are in place
+            const int own[4] = {oy0, oy1, oz0, oz1}, whole[4] = {0, T_[1], 0, T_[2]};
             a.fin[0] = oy0; a.fin[1] = oy1; a.fin[2] = oz0; a.fin[3] = oz1;
+            rects_clear(a); rects_add(a, oy0, oy1, oz0, oz1);
             mark(0); xpass(X_FWD, a, oz0, oz1);
             mark(11);
             (*psi_join)();
             psi_join = nullptr;
             a.fin[0] = a.fin[1] = 0;
             a.fout[0] = oy0; a.fout[1] = oy1; a.fout[2] = oz0; a.fout[3] = oz1;
+            rects_clear(a); rects_add_difference(a, whole, own);
             mark(0); xpass(X_FWD, a);
             a.fout[0] = a.fout[1] = 0;
+            rects_clear(a);
             mark(1); col(1, COL_FWD, nullptr);            // P2
         } else {
             if (psi_join && *psi_join) { (*psi_join)(); psi_join = nullptr; }
@@ -409,15 +432,28 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
             a.fin[0] = ey0; a.fin[1] = ey1; a.fin[2] = q0; a.fin[3] = q1;
             a.fkeep = 1;      // + the lines outside the volume (margins at volume faces): their quotient is 1, nobody delivers them
             if (deep) { a.fout[0] = dy0; a.fout[1] = dy1; a.fout[2] = dz0; a.fout[3] = dz1; }
+            {
+                // the same selection as rectangles: (own box, extended at faces) minus the deep interior, plus the interior-side halo rows
+                // of the planes that lie outside the volume in z
+                const int ext[4] = {ey0, ey1, q0, q1}, dp[4] = {dy0, dy1, dz0, dz1};
+                rects_clear(a);
+                if (deep) rects_add_difference(a, ext, dp); else rects_add(a, ey0, ey1, q0, q1);
+                const int vz0 = std::min(q1, std::max(q0, -t.org[2])), vz1 = std::max(q0, std::min(q1, g_.gdim[2] - t.org[2]));
+                rects_add(a, 0, ey0, q0, vz0); rects_add(a, ey1, T_[1], q0, vz0);
+                rects_add(a, 0, ey0, vz1, q1); rects_add(a, ey1, T_[1], vz1, q1);
+            }
             mark(4); xpass(X_RATIO, a, q0, q1);
             mark(9);
             a.fkeep = 0;
+            rects_clear(a);
             mid_exchange_(work_, t);
             if (deep) {
                 a.fout[0] = a.fout[1] = 0;
                 a.fin[0] = dy0; a.fin[1] = dy1; a.fin[2] = dz0; a.fin[3] = dz1;
+                rects_add(a, dy0, dy1, dz0, dz1);
                 mark(4); xpass(X_RATIO, a, dz0, dz1);
                 mark(9);
+                rects_clear(a);
             }
             a.fin[0] = a.fin[1] = a.fout[0] = a.fout[1] = 0;
             mid_join_();

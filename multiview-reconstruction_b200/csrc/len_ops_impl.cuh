@@ -209,13 +209,21 @@ __global__ void __launch_bounds__(32 * WPC, xw_min_blocks<P, WPC>()) x_kernel_w(
     if (HAS_IN && lane == 0) { tma::mbar_init(&bars[0], 1); tma::mbar_init(&bars[1], 1); tma::fence_mbar_init(); }
     __syncthreads();
 
-    const int nlines = a.line_end - a.line0;
+    // work items: the lines of the launch, or (nrect > 0) the lines of the selection rectangles; item k -> line index relative to line0
+    const int nlines = a.nrect > 0 ? a.rect_start[a.nrect] : a.line_end - a.line0;
     const int stride = (int)gridDim.x * WPC;
+    auto line_of = [&](int k) -> int {
+        if (a.nrect <= 0) return k;
+        int r = 0;
+        while (r + 1 < a.nrect && k >= a.rect_start[r + 1]) ++r;
+        const int kk = k - a.rect_start[r], w = a.rect[r][1] - a.rect[r][0];
+        return (a.rect[r][0] + kk % w) + a.ty * (a.rect[r][2] + kk / w) - a.line0;
+    };
     auto issue_load = [&](int ln, cpx* dst, unsigned long long* bar) {   // one lane
         tma::mbar_expect_tx(bar, LINE_BYTES);
         tma::load_bulk(dst, a.cdata + (long long)(a.line0 + ln) * a.px, LINE_BYTES, bar);
     };
-    int ln = (int)blockIdx.x * WPC + warp;
+    int k = (int)blockIdx.x * WPC + warp;
     unsigned par0 = 0, par1 = 0;
     WarpExec ex;
     // x range of the real rows this tile reads, as a 16-byte aligned byte range (bulk prefetch granularity); rows start 16-byte aligned
@@ -224,25 +232,29 @@ __global__ void __launch_bounds__(32 * WPC, xw_min_blocks<P, WPC>()) x_kernel_w(
     int pf_x1 = clampi(a.org[0] - a.goff[0] + 2 * M, 0, a.vol[0]);
     const unsigned pf_bytes = (unsigned)((pf_x1 - pf_x0) * 4) & ~15u;
     const bool pf_rows = a.pf_dist > 0 && (a.vol[0] & 3) == 0 && ((reinterpret_cast<unsigned long long>(a.src) & 15ull) == 0) && pf_bytes > 0;
-    // lines outside the responsibility box of the update / inverse pass are skipped (no load, no work)
-    const bool filtered = (KIND == X_UPDATE || KIND == X_INV) || a.fin[1] > a.fin[0] || a.fout[1] > a.fout[0];
-    auto has_work = [&](int l) -> bool {
-        if constexpr (KIND == X_UPDATE || KIND == X_INV) return x_line_in_box(a, a.line0 + l);
-        else return x_line_selected(a, a.line0 + l);
+    // lines outside the responsibility box of the update / inverse pass, or rejected by the line filter, are skipped (no load, no work);
+    // a rectangle list already holds the selected lines only
+    const bool filtered = a.nrect <= 0 && ((KIND == X_UPDATE || KIND == X_INV) || a.fin[1] > a.fin[0] || a.fout[1] > a.fout[0]);
+    auto has_work = [&](int kk) -> bool {
+        if constexpr (KIND == X_UPDATE || KIND == X_INV) return x_line_in_box(a, a.line0 + kk);
+        else return x_line_selected(a, a.line0 + kk);
     };
     if (filtered) {
-        while (ln < nlines && !has_work(ln)) ln += stride;
+        while (k < nlines && !has_work(k)) k += stride;
     }
-    if (HAS_IN && lane == 0 && ln < nlines) issue_load(ln, buf0, &bars[0]);
+    int ln = k < nlines ? line_of(k) : 0;
+    if (HAS_IN && lane == 0 && k < nlines) issue_load(ln, buf0, &bars[0]);
     double wsum = 0.0;
     float wmax = -1.f;
-    for (int it = 0; ln < nlines; ++it) {
+    for (int it = 0; k < nlines; ++it) {
         const int b = it & 1;
         cpx* const sm = b ? buf1 : buf0;
-        int nl = ln + stride;
+        int nk = k + stride;
         if (filtered) {
-            while (nl < nlines && !has_work(nl)) nl += stride;
+            while (nk < nlines && !has_work(nk)) nk += stride;
         }
+        const bool more = nk < nlines;
+        const int nl = more ? line_of(nk) : 0;
         // the pass stores into `sm` from its first phase on: the bulk store that last read this buffer (two lines ago) must be done
         if constexpr (HAS_OUT && !HAS_IN) { if (lane == 0) tma::wait_group_read<1>(); __syncwarp(); }
         if constexpr (HAS_IN) {
@@ -252,7 +264,7 @@ __global__ void __launch_bounds__(32 * WPC, xw_min_blocks<P, WPC>()) x_kernel_w(
             if constexpr (HAS_IN) {
                 if (lane == 0) {
                     if constexpr (HAS_OUT) tma::wait_group_read<0>();     // the other buffer's bulk store (previous line) has been read out
-                    if (nl < nlines) {
+                    if (more) {
                         issue_load(nl, b ? buf0 : buf1, &bars[b ^ 1]);
                         if constexpr (KIND == X_RATIO || KIND == X_UPDATE) {
                             // observed-image row of that line -> L2 (one bulk prefetch; rows outside the volume carry no data)
@@ -283,6 +295,7 @@ __global__ void __launch_bounds__(32 * WPC, xw_min_blocks<P, WPC>()) x_kernel_w(
             ex.unstash(lane, s, m);
             wsum += s; wmax = m > wmax ? m : wmax;
         }
+        k = nk;
         ln = nl;
     }
     if (HAS_OUT && lane == 0) tma::wait_group<0>();
@@ -402,7 +415,7 @@ struct LenImpl {
             MVD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d));
             slots[d & 63] = (per_sm > 0 ? per_sm : 1) * sms;
         }
-        const int nlines = a.line_end - a.line0;
+        const int nlines = a.nrect > 0 ? a.rect_start[a.nrect] : a.line_end - a.line0;
         int grid = slots[d & 63].load();
         if (grid <= 0) grid = 148;
         if (grid > (nlines + WPC - 1) / WPC) grid = (nlines + WPC - 1) / WPC;
