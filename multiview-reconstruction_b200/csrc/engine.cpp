@@ -147,6 +147,32 @@ struct ReduceParts2 {
     }
 };
 
+#ifndef MVD_HOST_EMU
+// ReduceParts1 + ReduceParts2 in one launch: the 256 lane sums go through shared memory instead of a second kernel (same order of
+// additions, hence the same bits; one launch and ~20 us less behind every view update)
+__global__ void __launch_bounds__(256) reduce_parts_kernel(ReduceParts1 r1, double* out) {
+    __shared__ double ss[256];
+    __shared__ float sm[256];
+    r1.ts = ss; r1.tm = sm;
+    r1((long long)threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ReduceParts2 r2{ss, sm, out};
+        r2(0);
+    }
+}
+#endif
+static void reduce_parts(stream_t s, const double* part_sum, const float* part_max, int nparts, double* scratch_sum, float* scratch_max, double* out) {
+#ifndef MVD_HOST_EMU
+    (void)scratch_sum; (void)scratch_max;
+    reduce_parts_kernel<<<1, 256, 0, s>>>(ReduceParts1{part_sum, part_max, nparts, nullptr, nullptr}, out);
+    MVD_CUDA_CHECK(cudaGetLastError());
+#else
+    pfor(256, ReduceParts1{part_sum, part_max, nparts, scratch_sum, scratch_max}, s);
+    pfor(1, ReduceParts2{scratch_sum, scratch_max, out}, s);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // Convolver
 // ------------------------------------------------------------------------------------------------
@@ -365,7 +391,10 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
         const int oz0 = std::max(0, g_.own_lo[2] - t.org[2]), oz1 = std::min(T_[2], g_.own_hi[2] - t.org[2]);
         a.src = psi_in;                                   // P1: mirror-single outside the volume (MultiViewDeconvolutionSeq.java:115)
         a.ext = EXT_MIRROR;
-        if (psi_join && *psi_join && chunk_planes_ == 0 && !std::getenv("MVD_DBG_NOP1SPLIT")) {
+        // MVD_SPLIT_P1=1: measured on c3 the two launches cost more (0.13 ms per view update at N = 2, 0.06 ms at N = 8) than the part of
+        // the psi exchange they hide -- most of it already travels behind the statistics kernel -- so the split is opt-in
+        static const bool split_p1 = [] { const char* e = std::getenv("MVD_SPLIT_P1"); return e && std::atoi(e) != 0; }();
+        if (psi_join && *psi_join && chunk_planes_ == 0 && split_p1) {
             // the halo exchange of psi is still travelling: the lines of the own box do not read halo data (a reflected row at a
             // volume face is an own row) and are transformed first; everything else follows once the halos are in place
             const int own[4] = {oy0, oy1, oz0, oz1}, whole[4] = {0, T_[1], 0, T_[2]};
@@ -409,7 +438,8 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
                 if (T_[2] - first > 0) dev::zero(work_ + (size_t)px_ * T_[1] * first, plane_bytes * (size_t)(T_[2] - first), stream_);
             }
         }
-        if (mid_exchange_ && mid_join_ && chunk_planes_ == 0 && !std::getenv("MVD_DBG_NOP5SPLIT")) {
+        static const bool split_p5 = [] { const char* e = std::getenv("MVD_SPLIT_P5"); return !(e && std::atoi(e) == 0); }();   // MVD_SPLIT_P5=0: A/B
+        if (mid_exchange_ && mid_join_ && chunk_planes_ == 0 && split_p5) {
             // Boundary-first quotient pass.  This rank computes the quotient on its own box, extended to the tile edge where the box
             // ends at a volume face (outside the volume the quotient is 1, and P5 writes exactly that); the neighbours deliver the
             // rest within the reach of kernel2, what lies beyond is cleared.  The lines the neighbours are waiting for -- own lines
@@ -1166,10 +1196,7 @@ void Engine::view_update(int v) {
     cur_ ^= 1;
     if (has_exchange()) start_psi_exchange(psi_[cur_]);   // travels behind the statistics kernels and the next update's first lines
     // deterministic two-level reduction of the per-CTA partial statistics
-    ReduceParts1 r1{part_sum_, part_max_, nparts, part_sum_ + nparts, part_max_ + nparts};
-    pfor(256, r1, stream_);
-    ReduceParts2 r2{part_sum_ + nparts, part_max_ + nparts, stats_dev_ + 2 * (size_t)stats_count_};
-    pfor(1, r2, stream_);
+    reduce_parts(stream_, part_sum_, part_max_, nparts, part_sum_ + nparts, part_max_ + nparts, stats_dev_ + 2 * (size_t)stats_count_);
     ++stats_count_;
 }
 

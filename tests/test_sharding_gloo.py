@@ -206,6 +206,7 @@ DIMS_2D = (40, 44, 24)
 
 
 def _worker_grid(rank, world, port, lib_path, out_dir, scheme):
+    os.environ["MVD_SPLIT_P1"] = "1"      # also cover the (opt-in) split of the forward pass around the psi exchange
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch.distributed as dist
