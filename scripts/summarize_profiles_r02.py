@@ -5,7 +5,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 def short(name):
-    m = re.search(r"(x_kernel_w|x_kernel_p|x_kernel|col_kernel)<.*?Plan<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+).*?>, \(int\)(\d)", name)
+    name = name.replace("(int)", "")
+    m = re.search(r"(x_kernel_w|x_kernel_p|x_kernel|col_kernel)<.*?Plan<(\d+), (\d+), (\d+), (\d+).*?>, (\d)", name)
     if m:
         kinds = {"x": ["X_FWD", "X_RATIO", "X_UPDATE", "X_INV"], "c": ["COL_FWD", "COL_INV", "COL_CONV"]}[m.group(1)[0]]
         return f"{m.group(1)}<N={m.group(2)} ({m.group(3)}x{m.group(4)}{'x' + m.group(5) if m.group(5) != '1' else ''}),{kinds[int(m.group(6))]}>"
@@ -24,17 +25,39 @@ for r in rows[1:]:
     a[0] += 1; a[1] += float(r[iv].replace(",", ""))
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(P, "launches_r02.md"), "w") as f:
-    f.write("# ncu launch list (round 2, final build)\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 1 --skip-e2e --skip-cpu --skip-parity`\n\n")
-    f.write("Cold-cache, serialised launch times: compare SHARES, not absolutes.  The first 400 launches cover the set-up (image synthesis convolutions, "
+    f.write("# ncu launch list (round 2, final build)\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv python bench.py --steps 2 --warmup 1 --skip-e2e --skip-cpu --skip-parity`\n\n")
+    f.write("Cold-cache, serialised launch times: compare SHARES, not absolutes.  The launches cover the set-up (image synthesis convolutions, "
             "PSF derivation, kernel spectra, weight masks, PsiInit), the warm-up and the timed steps.\n\n")
     f.write("| kernel | launches | total ns | share |\n|---|---:|---:|---:|\n")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"| `{k}` | {n} | {t:.0f} | {t / tot:.3f} |\n")
-    big = {k: v for k, v in agg.items() if "N=540" in k}
-    tb = sum(v[1] for v in big.values())
-    f.write("\nShares among the c3 tile kernels (FFT length 540) only -- to be compared with the CUDA-event shares of the bench line:\n\n| kernel | share |\n|---|---:|\n")
-    for k, (n, t) in sorted(big.items(), key=lambda kv: -kv[1][1]):
-        f.write(f"| `{k}` | {t / tb:.3f} |\n")
+    # share of one view update on one tile: mean launch time of each c3 tile kernel x its launches per view update, next to the
+    # CUDA-event shares of the committed bench line (all launches of a kernel name do the same work: same tile)
+    per_update = {"x_kernel_w<N=540 (18x30),X_FWD>": ("P1", 1), "col_kernel<N=540 (27x20),COL_FWD>": ("P2 + P6", 2),
+                  "col_kernel<N=540 (27x20),COL_CONV>": ("P3 + P7", 2), "col_kernel<N=540 (27x20),COL_INV>": ("P4 + P8", 2),
+                  "x_kernel_w<N=540 (18x30),X_RATIO>": ("P5", 1), "x_kernel<N=540 (18x30),X_UPDATE>": ("P9", 1)}
+    # only the launches of the two timed steps: the last 2 steps x 4 views x 2 tiles x 9 passes of the list (the same kernel names also
+    # serve the set-up -- spectra, PsiInit blur -- with other extension modes and cache states)
+    seq = [(short(r[ik]), float(r[iv].replace(",", ""))) for r in rows[1:] if len(r) > iv and r[im] == "gpu__time_duration.sum"]
+    tail = [x for x in seq if x[0] in per_update][-144:]
+    agg = collections.OrderedDict()
+    for k, t in tail:
+        a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += t
+    tb = sum(agg[k][1] / agg[k][0] * m for k, (_, m) in per_update.items() if k in agg)
+    ev = None
+    try:
+        line = json.loads([l for l in open(os.path.join(P, "bench_c3_n1_r02.json")).read().splitlines() if l.startswith("{")][-1])
+        pp = line["roofline"]["all_passes_ms_per_launch"]
+        ev = {"P1": pp[0], "P2 + P6": pp[1] + pp[5], "P3 + P7": pp[2] + pp[6], "P4 + P8": pp[3] + pp[7], "P5": pp[4], "P9": pp[8]}
+    except Exception:
+        pass
+    f.write("\nShare of one view update (c3 tile kernels, FFT length 540): ncu launch list vs the CUDA events of `bench_c3_n1_r02.json`:\n\n"
+            "| kernel | passes | launches in the two timed steps | ncu mean ns / launch | ncu share | CUDA-event share |\n|---|---|---:|---:|---:|---:|\n")
+    for k, (pas, m) in per_update.items():
+        if k in agg:
+            mean = agg[k][1] / agg[k][0]
+            es = f"{ev[pas] / sum(ev.values()):.3f}" if ev else "-"
+            f.write(f"| `{k}` | {pas} | {agg[k][0]} | {mean:.0f} | {mean * m / tb:.3f} | {es} |\n")
 shutil.copy(src, os.path.join(P, "launches_r02.csv"))
 
 # ---- ncu --set full of the nine passes ------------------------------------------------------------------------------------
