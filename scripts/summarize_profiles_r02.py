@@ -96,7 +96,7 @@ for pas, r in zip(names, rows[2:11]):
     traffic[pas] = rd + wr
 open(os.path.join(P, "ncu_r02.md"), "w").write("\n".join(out) + "\n")
 json.dump(traffic, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
-for a, b in (("final_bench_c3.json", "bench_c3_n1_r02.json"), ("final_bench_c2.json", "bench_c2_n1_r02.json"), ("prof_passes_c3.json", "passes_c3_r02.json"),
+for a, b in (("last_bench_c3.json", "bench_c3_n1_r02.json"), ("final_bench_c2.json", "bench_c2_n1_r02.json"), ("prof_passes_c3.json", "passes_c3_r02.json"),
              ("final_pytest.log", "pytest_gpu_r02.log"), ("final_smoke.log", "smoke_r02.log")):
     if os.path.exists(os.path.join(G, a)):
         lines = [l for l in open(os.path.join(G, a)).read().splitlines() if l.strip()]
