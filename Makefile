@@ -21,17 +21,17 @@ HDRS      := $(CSRC)/fft_codelets.cuh $(CSRC)/fft_passes.cuh $(CSRC)/backend.h $
 
 LENS      := $(shell MVD_LENGTHS="$(MVD_LENGTHS)" python3 $(CSRC)/gen_lengths.py $(GEN))
 LENOBJ    := $(foreach n,$(LENS),$(BUILD)/obj/len_$(n).o)
-OBJ       := $(LENOBJ) $(BUILD)/obj/registry.o $(BUILD)/obj/engine.o $(BUILD)/obj/pointwise.o $(BUILD)/obj/comm.o $(BUILD)/obj/psf_prep.o $(BUILD)/obj/tiff_io.o $(BUILD)/obj/capi.o
+OBJ       := $(LENOBJ) $(BUILD)/obj/registry.o $(BUILD)/obj/engine.o $(BUILD)/obj/pointwise.o $(BUILD)/obj/comm.o $(BUILD)/obj/psf_prep.o $(BUILD)/obj/tiff_io.o $(BUILD)/obj/n5_io.o $(BUILD)/obj/capi.o
 
 HLENS     := $(shell MVD_LENGTHS="$(HOSTEMU_LENGTHS)" python3 $(CSRC)/gen_lengths.py $(GENH))
 HLENOBJ   := $(foreach n,$(HLENS),$(BUILD)/hostemu/obj/len_$(n).o)
-HOBJ      := $(HLENOBJ) $(BUILD)/hostemu/obj/registry.o $(BUILD)/hostemu/obj/engine.o $(BUILD)/hostemu/obj/pointwise.o $(BUILD)/hostemu/obj/comm.o $(BUILD)/hostemu/obj/psf_prep.o $(BUILD)/hostemu/obj/tiff_io.o $(BUILD)/hostemu/obj/capi.o
+HOBJ      := $(HLENOBJ) $(BUILD)/hostemu/obj/registry.o $(BUILD)/hostemu/obj/engine.o $(BUILD)/hostemu/obj/pointwise.o $(BUILD)/hostemu/obj/comm.o $(BUILD)/hostemu/obj/psf_prep.o $(BUILD)/hostemu/obj/tiff_io.o $(BUILD)/hostemu/obj/n5_io.o $(BUILD)/hostemu/obj/capi.o
 
 .PHONY: all hostemu clean fft_emu_test
 all: $(PKG)/libmvdecon.so
 
 $(PKG)/libmvdecon.so: $(OBJ)
-	$(NVCC) -shared -o $@ $(OBJ) -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -lcudart -ldl
+	$(NVCC) -shared -o $@ $(OBJ) -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -lcudart -ldl -lz
 
 $(BUILD)/obj/len_%.o: $(GEN)/len_%.cu $(HDRS)
 	@mkdir -p $(BUILD)/obj $(BUILD)/ptxas
@@ -54,13 +54,16 @@ $(BUILD)/obj/psf_prep.o: $(CSRC)/psf_prep.cpp $(HDRS)
 $(BUILD)/obj/tiff_io.o: $(CSRC)/tiff_io.cpp $(HDRS)
 	@mkdir -p $(BUILD)/obj
 	$(NVCC) $(NVFLAGS) -I$(CSRC) -x cu -c $< -o $@ 2> /dev/null
+$(BUILD)/obj/n5_io.o: $(CSRC)/n5_io.cpp $(HDRS)
+	@mkdir -p $(BUILD)/obj
+	$(NVCC) $(NVFLAGS) -I$(CSRC) -x cu -c $< -o $@ 2> /dev/null
 $(BUILD)/obj/capi.o: $(CSRC)/capi.cpp $(HDRS)
 	@mkdir -p $(BUILD)/obj
 	$(NVCC) $(NVFLAGS) -I$(CSRC) -x cu -c $< -o $@ 2> $(BUILD)/ptxas_capi.log || (cat $(BUILD)/ptxas_capi.log; false)
 
 hostemu: tests/host/libmvdecon_hostemu.so
 tests/host/libmvdecon_hostemu.so: $(HOBJ)
-	$(CXX) -shared -o $@ $(HOBJ)
+	$(CXX) -shared -o $@ $(HOBJ) -lz
 $(BUILD)/hostemu/obj/len_%.o: $(GENH)/len_%.cu $(HDRS)
 	@mkdir -p $(BUILD)/hostemu/obj
 	$(CXX) $(HOSTFLAGS) -x c++ -c $< -o $@
@@ -80,6 +83,9 @@ $(BUILD)/hostemu/obj/psf_prep.o: $(CSRC)/psf_prep.cpp $(HDRS)
 	@mkdir -p $(BUILD)/hostemu/obj
 	$(CXX) $(HOSTFLAGS) -x c++ -c $< -o $@
 $(BUILD)/hostemu/obj/tiff_io.o: $(CSRC)/tiff_io.cpp $(HDRS)
+	@mkdir -p $(BUILD)/hostemu/obj
+	$(CXX) $(HOSTFLAGS) -x c++ -c $< -o $@
+$(BUILD)/hostemu/obj/n5_io.o: $(CSRC)/n5_io.cpp $(HDRS)
 	@mkdir -p $(BUILD)/hostemu/obj
 	$(CXX) $(HOSTFLAGS) -x c++ -c $< -o $@
 $(BUILD)/hostemu/obj/capi.o: $(CSRC)/capi.cpp $(HDRS)

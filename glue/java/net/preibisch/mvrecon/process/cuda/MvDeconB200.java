@@ -88,6 +88,9 @@ public interface MvDeconB200 extends CUDAFourierConvolution
 	int mvd_run_iterations( Pointer ctx, int n, double[] stats );
 	int mvd_run_iteration_mul( Pointer ctx, double[] stats );
 	int mvd_tiff_write( String path, float[] data, int[] dimsXYZ );
+	int mvd_n5_dims( String datasetDir, int[] dimsXYZ );
+	int mvd_n5_read( String datasetDir, float[] out );
+	int mvd_n5_write( String datasetDir, float[] data, int[] dimsXYZ, int[] blockSizeXYZ, int gzipLevel );
 
 	// ---- multi-GPU: one context per device, halos exchanged by the library ----
 	int mvd_comm_unique_id( byte[] id128 );

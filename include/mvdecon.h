@@ -151,6 +151,14 @@ MVD_API int mvd_psi_init_from_file(mvd_context* ctx, const char* path, int preci
 MVD_API int mvd_tiff_dims(const char* path, int dims[3]);
 MVD_API int mvd_tiff_read(const char* path, float* out);
 MVD_API int mvd_tiff_write(const char* path, const float* data, const int dims[3]);
+/* N5 datasets at the same boundary (file-system N5 format restated, github.com/saalfeldlab/n5): dataset_dir = <container>/<dataset>.
+ * mvd_n5_dims / mvd_n5_read: what PointSpreadFunction.load does for "psf.n5" (M/fiji/spimdata/pointspreadfunctions/PointSpreadFunction.java:
+ * 119-137; N5Utils.open): any 3-d dataset of uint8 / int8 / uint16 / int16 / uint32 / int32 / float32 / float64, raw or gzip, as float32,
+ * dims (x,y,z), missing blocks = 0 -- the result feeds mvd_set_psf.  mvd_n5_write: PointSpreadFunction.save (:139-162: block 128^3, gzip
+ * level 1) and the N5 export of the deconvolved volume (M/process/export/ExportN5Api.java): float32, gzip_level 0..9 or < 0 = raw.        */
+MVD_API int mvd_n5_dims(const char* dataset_dir, int dims[3]);
+MVD_API int mvd_n5_read(const char* dataset_dir, float* out);
+MVD_API int mvd_n5_write(const char* dataset_dir, const float* data, const int dims[3], const int block_size[3], int gzip_level);
 
 /* Weight masks on the device.  mvd_make_blending_weights: cosine blending of view v's axis-aligned box [box_min, box_max] (global
  * integer coordinates, inclusive; BlendingRealRandomAccess.computeWeight, M/process/fusion/transformed/weights/BlendingRealRandomAccess.java:95-130)

@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
+import math
 import os
 from typing import List, Optional, Sequence, Tuple
 
@@ -135,6 +136,9 @@ SYMBOLS = {
     "mvd_tiff_dims": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "mvd_tiff_read": (C.c_int, [C.c_char_p, _F]),
     "mvd_tiff_write": (C.c_int, [C.c_char_p, _F, C.POINTER(C.c_int)]),
+    "mvd_n5_dims": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
+    "mvd_n5_read": (C.c_int, [C.c_char_p, _F]),
+    "mvd_n5_write": (C.c_int, [C.c_char_p, _F, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
     "mvd_plan_axis": (C.c_int, [C.c_int] * 10 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
     "mvd_fuse_group": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_RawView), C.c_int, C.POINTER(C.c_int), C.c_float, C.c_float]),
     "mvd_last_fuse_group_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
@@ -250,6 +254,19 @@ class Lib:
     def tiff_write(self, path: str, vol: np.ndarray) -> None:
         vol = _f32(vol)
         self.check(self.dll.mvd_tiff_write(os.fsencode(path), _fp(vol), _i3(_xyz(vol))))
+
+    def n5_read(self, dataset_dir: str) -> np.ndarray:
+        """an N5 dataset (raw / gzip, any integer or float element type) as float32, [z, y, x] -- N5Utils.open of PointSpreadFunction.load"""
+        d = (C.c_int * 3)()
+        self.check(self.dll.mvd_n5_dims(os.fsencode(dataset_dir), d))
+        out = np.empty((d[2], d[1], d[0]), dtype=np.float32)
+        self.check(self.dll.mvd_n5_read(os.fsencode(dataset_dir), _fp(out)))
+        return out
+
+    def n5_write(self, dataset_dir: str, vol: np.ndarray, blockSize_xyz=(128, 128, 128), gzip_level: int = 1) -> None:
+        """float32 N5 dataset; the defaults are those of PointSpreadFunction.save (128^3 blocks, GzipCompression(1)); gzip_level < 0 = raw"""
+        vol = _f32(vol)
+        self.check(self.dll.mvd_n5_write(os.fsencode(dataset_dir), _fp(vol), _i3(_xyz(vol)), _i3(blockSize_xyz), int(gzip_level)))
 
     def plan_axis(self, gdim: int, own_lo: int, own_hi: int, r1=(0, 0), r2=(0, 0), is_x: bool = False, max_fft_len: int = 0,
                   two_exchanges: bool = False):
@@ -767,9 +784,34 @@ class MultiViewDeconvolutionSeq:
             self.lib.check(self.lib.dll.mvd_set_max_intensities(views._ctx, _fp(self.max)))
             self.lib.check(self.lib.dll.mvd_set_psi(views._ctx, _fp(psiInit.psi0)))
         self.stats: List[List[IterationStatistics]] = []
+        self.debug, self.debugInterval, self._debugSink = False, 1, None
+        self.debugStack: List[Tuple[int, np.ndarray]] = []
 
     def initWasSuccessful(self) -> bool:
         return self.max is not None
+
+    # ---- debug view (MultiViewDeconvolution.java:119-122, 153-191): a copy of psi every debugInterval iterations ------------------
+    def setDebug(self, debug: bool, sink=None) -> None:
+        """sink(iteration, psi_copy) replaces the default, which appends to debugStack (the reference appends slices to an ImageStack)"""
+        self.debug, self._debugSink = bool(debug), sink
+
+    def setDebugInterval(self, debugInterval: int) -> None:
+        self.debugInterval = int(debugInterval)
+
+    def getDebugImage(self) -> List[Tuple[int, np.ndarray]]:
+        return self.debugStack
+
+    def _debug_due(self) -> bool:
+        # `debug && ( it-1 ) % debugInterval == 0` with Java's remainder (sign of the dividend): before the first iteration it only
+        # fires for debugInterval == 1
+        return self.debug and int(math.fmod(self.it - 1, self.debugInterval)) == 0
+
+    def _debug_show(self) -> None:
+        psi = self.getPSI()                                    # never the live image: it is being updated (MultiViewDeconvolution.java:158-160)
+        if self._debugSink is not None:
+            self._debugSink(self.it, psi)
+        else:
+            self.debugStack.append((self.it, psi))
 
     def runNextIteration(self) -> List[IterationStatistics]:
         self.it += 1
@@ -782,6 +824,14 @@ class MultiViewDeconvolutionSeq:
         return out
 
     def runIterations(self) -> None:
+        if self.max is None:                                   # MultiViewDeconvolution.java:146-147
+            return
+        if self.debug:                                         # iteration by iteration, psi copied out where the reference shows it
+            while self.it < self.numIterations:
+                if self._debug_due():
+                    self._debug_show()
+                self.runNextIteration()
+            return
         n = self.numIterations - self.it
         if n <= 0:
             return
@@ -814,7 +864,11 @@ class MultiViewDeconvolutionMul(MultiViewDeconvolutionSeq):
         return out
 
     def runIterations(self) -> None:
+        if self.max is None:
+            return
         while self.it < self.numIterations:
+            if self._debug_due():
+                self._debug_show()
             self.runNextIteration()
 
 

@@ -359,6 +359,20 @@ int mvd_tiff_read(const char* path, float* out) {
 int mvd_tiff_write(const char* path, const float* data, const int dims[3]) {
     return guarded([&] { require(path && data && dims, "null argument"); tiff_write_f32(path, data, dims); });
 }
+int mvd_n5_dims(const char* dataset_dir, int dims[3]) {
+    return guarded([&] { require(dataset_dir && dims, "null argument"); n5_dims(dataset_dir, dims); });
+}
+int mvd_n5_read(const char* dataset_dir, float* out) {
+    return guarded([&] {
+        require(dataset_dir && out, "null argument");
+        int d[3];
+        const std::vector<float> img = n5_read_f32(dataset_dir, d);
+        std::copy(img.begin(), img.end(), out);
+    });
+}
+int mvd_n5_write(const char* dataset_dir, const float* data, const int dims[3], const int block_size[3], int gzip_level) {
+    return guarded([&] { require(dataset_dir && data && dims && block_size, "null argument"); n5_write_f32(dataset_dir, data, dims, block_size, gzip_level); });
+}
 int mvd_plan_axis(int gdim, int own_lo, int own_hi, int r1_lo, int r1_hi, int r2_lo, int r2_hi, int is_x, int max_fft_len, int two_exchanges,
                   int* tile_len, int* tiles, int cap, int* num_tiles) {
     return guarded([&] {

@@ -242,6 +242,10 @@ std::vector<float> psf_transform_normalized(const float* psf, const int dims[3],
 std::vector<float> psf_average(const float* const* psfs, const int (*dims)[3], int count, bool use_max, int out_dims[3]);
 std::vector<float> psf_make_same_size(const float* psf, const int dims[3], const int new_dims[3]);
 // TIFF stacks at the boundary (tiff_io.cpp): PsiInitFromFile / Save3dTIFF
+// N5 datasets (csrc/n5_io.cpp): the project's PSF store (psf.n5) and the N5 export of the result; dims (x,y,z)
+void n5_dims(const char* dataset_dir, int dims[3]);
+std::vector<float> n5_read_f32(const char* dataset_dir, int dims[3]);
+void n5_write_f32(const char* dataset_dir, const float* data, const int dims[3], const int block[3], int gzip_level);
 void tiff_dims(const char* path, int dims[3]);
 std::vector<float> tiff_read_f32(const char* path, int dims[3]);
 void tiff_write_f32(const char* path, const float* data, const int dims[3]);

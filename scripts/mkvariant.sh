@@ -14,6 +14,6 @@ nvcc $FLAGS "$@" -c $D/len_$N.cu -o $D/len_$N.o 2> $D/ptxas.log
 nvcc $FLAGS -x cu -c $D/gen/registry.cpp -o $D/registry.o 2> /dev/null
 OBJS=""
 for n in $SUB; do [ "$n" != "$N" ] && OBJS="$OBJS build/obj/len_$n.o"; done
-for o in engine pointwise comm psf_prep tiff_io capi; do OBJS="$OBJS build/obj/$o.o"; done
-nvcc -shared -o variants/libmvdecon_$NAME.so $OBJS $D/registry.o $D/len_$N.o -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -lcudart -ldl
+for o in engine pointwise comm psf_prep tiff_io n5_io capi; do OBJS="$OBJS build/obj/$o.o"; done
+nvcc -shared -o variants/libmvdecon_$NAME.so $OBJS $D/registry.o $D/len_$N.o -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -lcudart -ldl -lz
 grep -E "registers|spill" $D/ptxas.log | paste - - | awk '{print $5,$9,"|",$16,$17}' | tr '\n' ';'; echo

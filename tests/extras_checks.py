@@ -303,3 +303,111 @@ def check_filter_blocks_mirror():
     assert removed == n_before - expect_keep and removed > 0
     assert sum(len(b) for b in batches) == expect_keep and all(len(b) > 0 for b in batches)
     assert all(m.blockContainsContent(b, w) for batch in batches for b in batch)
+
+
+# ---- N5 datasets (PointSpreadFunction.load / save, N5 export) -----------------------------------------------------------------------
+def _n5_write_reference(path, vol, block_xyz, dtype=">f4", compression="gzip"):
+    """An independent writer of the published N5 file-system format (numpy + gzip + struct), used to check the library's reader."""
+    import gzip, json, os, struct
+    nz, ny, nx = vol.shape
+    os.makedirs(path, exist_ok=True)
+    name = {">f4": "float32", ">u2": "uint16", ">u1": "uint8", ">f8": "float64", ">i2": "int16"}[dtype]
+    comp = {"type": "gzip", "useZlib": False, "level": 1} if compression == "gzip" else {"type": "raw"}
+    with open(os.path.join(path, "attributes.json"), "w") as f:
+        json.dump({"dimensions": [nx, ny, nz], "blockSize": list(block_xyz), "dataType": name, "compression": comp}, f)
+    bx, by, bz = block_xyz
+    for gz in range(-(-nz // bz)):
+        for gy in range(-(-ny // by)):
+            for gx in range(-(-nx // bx)):
+                blk = vol[gz * bz:(gz + 1) * bz, gy * by:(gy + 1) * by, gx * bx:(gx + 1) * bx]
+                if gz == 1 and gy == 0 and gx == 0 and not blk.any():
+                    continue                                        # a missing block reads as zeros
+                payload = np.ascontiguousarray(blk).astype(dtype).tobytes()        # x fastest, big endian
+                if compression == "gzip":
+                    payload = gzip.compress(payload, 1)
+                hdr = struct.pack(">HHIII", 0, 3, blk.shape[2], blk.shape[1], blk.shape[0])
+                d = os.path.join(path, str(gx), str(gy))
+                os.makedirs(d, exist_ok=True)
+                with open(os.path.join(d, str(gz)), "wb") as f:
+                    f.write(hdr + payload)
+
+
+def _n5_read_reference(path):
+    import gzip, json, os, struct
+    a = json.load(open(os.path.join(path, "attributes.json")))
+    nx, ny, nz = a["dimensions"]
+    bx, by, bz = a["blockSize"]
+    assert a["dataType"] == "float32"
+    out = np.zeros((nz, ny, nx), dtype=np.float32)
+    for gz in range(-(-nz // bz)):
+        for gy in range(-(-ny // by)):
+            for gx in range(-(-nx // bx)):
+                fn = os.path.join(path, str(gx), str(gy), str(gz))
+                if not os.path.exists(fn):
+                    continue
+                raw = open(fn, "rb").read()
+                mode, nd, sx, sy, sz = struct.unpack(">HHIII", raw[:16])
+                assert mode == 0 and nd == 3
+                payload = raw[16:]
+                if a["compression"]["type"] == "gzip":
+                    assert payload[:2] == b"\x1f\x8b"               # a gzip member, as N5's GzipCompression writes
+                    payload = gzip.decompress(payload)
+                blk = np.frombuffer(payload, dtype=">f4").reshape(sz, sy, sx)
+                out[gz * bz:gz * bz + sz, gy * by:gy * by + sy, gx * bx:gx * bx + sx] = blk
+    return out, a
+
+
+def check_n5_io(lib, tmp_path):
+    """mvd_n5_read / mvd_n5_write against an independent implementation of the N5 file-system format: several blocks with truncated edge
+    blocks, raw and gzip, integer and floating element types, a missing block; and the PSF round trip of PointSpreadFunction.save / load."""
+    import os
+    rng = np.random.default_rng(11)
+    vol = rng.random((21, 19, 37), dtype=np.float32) * 1000 - 200
+    vol[16:, :8, :16] = 0.0                                          # block (0, 0, 1) of the 16 x 8 x 16 grid is empty -> not written
+    # reader: files written by the independent writer
+    for k, (dtype, comp) in enumerate([(">f4", "gzip"), (">f4", "raw"), (">u2", "gzip"), (">f8", "raw"), (">i2", "gzip"), (">u1", "raw")]):
+        d = os.path.join(str(tmp_path), f"ds{k}")
+        src = vol if dtype in (">f4", ">f8") else np.clip(np.round(vol), 0 if dtype != ">i2" else -200, 255 if dtype == ">u1" else 800)
+        _n5_write_reference(d, src, (16, 8, 16), dtype, comp)
+        got = lib.n5_read(d)
+        assert got.shape == vol.shape
+        assert np.array_equal(got, src.astype(dtype).astype(np.float32))
+    # writer: read back by the independent reader and by the library
+    for level in (1, -1, 6):
+        d = os.path.join(str(tmp_path), f"out{level}")
+        lib.n5_write(d, vol, (16, 8, 16), level)
+        back, attrs = _n5_read_reference(d)
+        assert np.array_equal(back, vol) and attrs["dimensions"] == [37, 19, 21] and attrs["blockSize"] == [16, 8, 16]
+        assert attrs["compression"]["type"] == ("raw" if level < 0 else "gzip")
+        assert np.array_equal(lib.n5_read(d), vol)
+    # PointSpreadFunction.save -> load: one 128^3 gzip-1 block for a PSF
+    psf = rng.random((25, 19, 25), dtype=np.float32)
+    d = os.path.join(str(tmp_path), "psf.n5", "psf_t0_v3")
+    lib.n5_write(d, psf)
+    assert np.array_equal(lib.n5_read(d), psf) and os.path.exists(os.path.join(d, "0", "0", "0"))
+    with pytest.raises(Exception):
+        lib.n5_read(os.path.join(str(tmp_path), "nothing_here"))
+
+
+def check_debug_interval(lib, oracle, small_dataset):
+    """MultiViewDeconvolution.setDebug / setDebugInterval (MultiViewDeconvolution.java:119-122,153-191): psi is copied out before the
+    iterations it with (it - 1) % debugInterval == 0 (Java remainder), and the run itself is unchanged."""
+    import mvrecon_b200 as m
+    ds = small_dataset
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN)
+    mx = [v.max_intensity for v in views]
+    res = []
+    for interval in (None, 1, 2):
+        dv = m.DeconViews([m.DeconView(ds.images[v], ds.weights[v], ds.psfs[v], m.PSFTYPE.EFFICIENT_BAYESIAN) for v in range(3)], library=lib)
+        try:
+            dec = m.MultiViewDeconvolutionSeq(dv, 4, m.PsiInitFromRAI(psi0, mx))
+            if interval is not None:
+                dec.setDebug(True)
+                dec.setDebugInterval(interval)
+            dec.runIterations()
+            res.append((dec.getPSI(), [it for it, _ in dec.getDebugImage()], [p for _, p in dec.getDebugImage()]))
+        finally:
+            dv.close()
+    assert res[0][1] == [] and res[1][1] == [0, 1, 2, 3] and res[2][1] == [1, 3]
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][0], res[2][0])
+    assert np.array_equal(res[1][2][0], psi0) and np.array_equal(res[1][2][1], res[2][2][0])

@@ -43,3 +43,11 @@ def test_skip_empty_tiles(product_lib, oracle):
 
 def test_tiff_io_and_psi_init_from_file(product_lib, oracle, small_dataset, tmp_path):
     X.check_tiff_io_and_psi_init_from_file(product_lib, oracle, small_dataset, tmp_path)
+
+
+def test_n5_io(product_lib, tmp_path):
+    X.check_n5_io(product_lib, tmp_path)
+
+
+def test_debug_interval(product_lib, oracle, small_dataset):
+    X.check_debug_interval(product_lib, oracle, small_dataset)

@@ -45,3 +45,11 @@ def test_skip_empty_tiles(hostemu_lib, oracle):
 
 def test_filter_blocks_mirror():
     X.check_filter_blocks_mirror()
+
+
+def test_n5_io(hostemu_lib, tmp_path):
+    X.check_n5_io(hostemu_lib, tmp_path)
+
+
+def test_debug_interval(hostemu_lib, oracle, small_dataset):
+    X.check_debug_interval(hostemu_lib, oracle, small_dataset)
