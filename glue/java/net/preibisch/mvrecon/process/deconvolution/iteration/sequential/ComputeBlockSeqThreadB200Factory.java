@@ -36,6 +36,10 @@ public class ComputeBlockSeqThreadB200Factory implements ComputeBlockThreadFacto
 	@Override
 	public int numParallelBlocks() { return idToCudaDevice.keySet().size(); }
 
+	/** the loaded library and the first selected device, for the resident driver (MultiViewDeconvolutionB200) */
+	public MvDeconB200 lib() { return lib; }
+	public int firstDeviceId() { return idToCudaDevice.get( 0 ).getDeviceId(); }
+
 	@Override
 	public String toString()
 	{
