@@ -132,9 +132,10 @@ HaloComm::~HaloComm() {
     close_peer();
 }
 
-void HaloComm::reserve(size_t floats) {
+void HaloComm::reserve(size_t floats, stream_t also) {
     if (floats <= stage_floats_) return;
     dev::sync(stream_);
+    if (also && also != stream_) dev::sync(also);          // an earlier exchange on the exchange stream may still read the old buffers
     for (float*& p : stage_) { dev::free_(p); p = (float*)dev::alloc(sizeof(float) * floats); }
     stage_floats_ = floats;
 }
@@ -182,7 +183,7 @@ void HaloComm::exchange_nccl(const HaloBox& b, stream_t xs) {
     if (py_ > 1 && (b.hy_lo > 0 || b.hy_hi > 0)) {
         const bool lower = ry_ > 0, upper = ry_ < py_ - 1;
         const size_t per_row = (size_t)b.row_floats * (size_t)(b.z1 - b.z0);
-        reserve((size_t)std::max(b.hy_lo, b.hy_hi) * per_row);
+        reserve((size_t)std::max(b.hy_lo, b.hy_hi) * per_row, xs);
         const size_t cnt_lo = (size_t)b.hy_lo * per_row, cnt_hi = (size_t)b.hy_hi * per_row;
         if (lower) pack_rows(b, stage_[0], b.y0, b.hy_hi, 1, xs);
         if (upper) pack_rows(b, stage_[1], b.y1 - b.hy_lo, b.hy_lo, 1, xs);

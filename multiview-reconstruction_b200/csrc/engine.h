@@ -186,7 +186,7 @@ class HaloComm {
     void all_reduce(double* host_values, int count, int op);      // collective, synchronises the stream; op 0 sum, 1 max
     int transport() const { return peer_ ? 1 : 0; }      // 0: NCCL send/recv, 1: direct stores into the neighbours' memory
   private:
-    void reserve(size_t floats);
+    void reserve(size_t floats, stream_t also = nullptr);
     void exchange_nccl(const HaloBox& b, stream_t s);
     void exchange_peer(const HaloBox& b, stream_t s);
     void setup_peer(size_t need_y, size_t need_z);
