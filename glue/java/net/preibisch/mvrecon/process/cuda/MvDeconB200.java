@@ -91,6 +91,7 @@ public interface MvDeconB200 extends CUDAFourierConvolution
 	int mvd_n5_dims( String datasetDir, int[] dimsXYZ );
 	int mvd_n5_read( String datasetDir, float[] out );
 	int mvd_n5_write( String datasetDir, float[] data, int[] dimsXYZ, int[] blockSizeXYZ, int gzipLevel );
+	int mvd_zarr_write( String path, float[] data, int[] dimsXYZ, int[] chunkSizeXYZ, int gzipLevel, double[] voxelSizeXYZ );
 
 	// ---- multi-GPU: one context per device, halos exchanged by the library ----
 	int mvd_comm_unique_id( byte[] id128 );

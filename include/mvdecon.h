@@ -159,6 +159,9 @@ MVD_API int mvd_tiff_write(const char* path, const float* data, const int dims[3
 MVD_API int mvd_n5_dims(const char* dataset_dir, int dims[3]);
 MVD_API int mvd_n5_read(const char* dataset_dir, float* out);
 MVD_API int mvd_n5_write(const char* dataset_dir, const float* data, const int dims[3], const int block_size[3], int gzip_level);
+/* OME-Zarr (NGFF 0.4, Zarr v2, one resolution level "0", axes z y x, gzip or raw chunks, "/" separator) export of the result -- the
+ * other container ExportN5Api writes; dims / chunk_size (x,y,z), voxel_size (x,y,z) in micrometers or NULL.                          */
+MVD_API int mvd_zarr_write(const char* path, const float* data, const int dims[3], const int chunk_size[3], int gzip_level, const double voxel_size[3]);
 
 /* Weight masks on the device.  mvd_make_blending_weights: cosine blending of view v's axis-aligned box [box_min, box_max] (global
  * integer coordinates, inclusive; BlendingRealRandomAccess.computeWeight, M/process/fusion/transformed/weights/BlendingRealRandomAccess.java:95-130)

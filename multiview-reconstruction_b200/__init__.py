@@ -139,6 +139,7 @@ SYMBOLS = {
     "mvd_n5_dims": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "mvd_n5_read": (C.c_int, [C.c_char_p, _F]),
     "mvd_n5_write": (C.c_int, [C.c_char_p, _F, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
+    "mvd_zarr_write": (C.c_int, [C.c_char_p, _F, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, _D]),
     "mvd_plan_axis": (C.c_int, [C.c_int] * 10 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
     "mvd_fuse_group": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_RawView), C.c_int, C.POINTER(C.c_int), C.c_float, C.c_float]),
     "mvd_last_fuse_group_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
@@ -267,6 +268,12 @@ class Lib:
         """float32 N5 dataset; the defaults are those of PointSpreadFunction.save (128^3 blocks, GzipCompression(1)); gzip_level < 0 = raw"""
         vol = _f32(vol)
         self.check(self.dll.mvd_n5_write(os.fsencode(dataset_dir), _fp(vol), _i3(_xyz(vol)), _i3(blockSize_xyz), int(gzip_level)))
+
+    def zarr_write(self, path: str, vol: np.ndarray, chunk_xyz=(128, 128, 128), gzip_level: int = 1, voxel_size_xyz=None) -> None:
+        """OME-Zarr 0.4 group with one level "0" (Zarr v2, gzip or raw chunks)"""
+        vol = _f32(vol)
+        vs = None if voxel_size_xyz is None else (C.c_double * 3)(*[float(v) for v in voxel_size_xyz])
+        self.check(self.dll.mvd_zarr_write(os.fsencode(path), _fp(vol), _i3(_xyz(vol)), _i3(chunk_xyz), int(gzip_level), vs))
 
     def plan_axis(self, gdim: int, own_lo: int, own_hi: int, r1=(0, 0), r2=(0, 0), is_x: bool = False, max_fft_len: int = 0,
                   two_exchanges: bool = False):

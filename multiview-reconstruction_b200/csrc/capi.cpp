@@ -373,6 +373,9 @@ int mvd_n5_read(const char* dataset_dir, float* out) {
 int mvd_n5_write(const char* dataset_dir, const float* data, const int dims[3], const int block_size[3], int gzip_level) {
     return guarded([&] { require(dataset_dir && data && dims && block_size, "null argument"); n5_write_f32(dataset_dir, data, dims, block_size, gzip_level); });
 }
+int mvd_zarr_write(const char* path, const float* data, const int dims[3], const int chunk_size[3], int gzip_level, const double voxel_size[3]) {
+    return guarded([&] { require(path && data && dims && chunk_size, "null argument"); zarr_write_f32(path, data, dims, chunk_size, gzip_level, voxel_size); });
+}
 int mvd_plan_axis(int gdim, int own_lo, int own_hi, int r1_lo, int r1_hi, int r2_lo, int r2_hi, int is_x, int max_fft_len, int two_exchanges,
                   int* tile_len, int* tiles, int cap, int* num_tiles) {
     return guarded([&] {

@@ -246,6 +246,7 @@ std::vector<float> psf_make_same_size(const float* psf, const int dims[3], const
 void n5_dims(const char* dataset_dir, int dims[3]);
 std::vector<float> n5_read_f32(const char* dataset_dir, int dims[3]);
 void n5_write_f32(const char* dataset_dir, const float* data, const int dims[3], const int block[3], int gzip_level);
+void zarr_write_f32(const char* path, const float* data, const int dims[3], const int chunk[3], int gzip_level, const double* voxel_size);
 void tiff_dims(const char* path, int dims[3]);
 std::vector<float> tiff_read_f32(const char* path, int dims[3]);
 void tiff_write_f32(const char* path, const float* data, const int dims[3]);

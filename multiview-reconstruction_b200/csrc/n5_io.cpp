@@ -255,4 +255,65 @@ void n5_write_f32(const char* dataset_dir, const float* data, const int dims[3],
             }
 }
 
+// OME-Zarr (NGFF 0.4) export of the result, the second container format of ExportN5Api (M/process/export/ExportN5Api.java; n5-zarr is
+// third-party): a Zarr v2 group with one multiscale level,
+//   <path>/.zgroup   {"zarr_format":2}
+//   <path>/.zattrs   {"multiscales":[{"version":"0.4","axes":[z,y,x (space, micrometer)],"datasets":[{"path":"0","coordinateTransformations":[scale]}]}]}
+//   <path>/0/.zarray {"zarr_format":2,"shape":[z,y,x],"chunks":[cz,cy,cx],"dtype":"<f4","order":"C","fill_value":0,"dimension_separator":"/",
+//                     "compressor":null | {"id":"gzip","level":L},"filters":null}
+//   <path>/0/<iz>/<iy>/<ix>   every chunk in full chunk size (edge chunks padded with the fill value), C order, little endian, gzip'ed or raw
+void zarr_write_f32(const char* path, const float* data, const int dims[3], const int chunk[3], int gzip_level, const double* voxel_size) {
+    const std::string dir = path;
+    for (int i = 0; i < 3; ++i)
+        if (dims[i] < 1 || chunk[i] < 1) throw Error("Zarr: bad dimensions / chunk size");
+    if (gzip_level > 9) gzip_level = 9;
+    const std::string arr = dir + "/0";
+    mkdirs(arr);
+    auto put_file = [](const std::string& fn, const std::string& text) {
+        FILE* f = std::fopen(fn.c_str(), "wb");
+        if (!f) throw Error("Zarr: cannot write " + fn);
+        std::fwrite(text.data(), 1, text.size(), f);
+        std::fclose(f);
+    };
+    const double vs[3] = {voxel_size ? voxel_size[0] : 1.0, voxel_size ? voxel_size[1] : 1.0, voxel_size ? voxel_size[2] : 1.0};
+    put_file(dir + "/.zgroup", "{\"zarr_format\":2}");
+    char scale[160];
+    std::snprintf(scale, sizeof(scale), "[%.17g,%.17g,%.17g]", vs[2], vs[1], vs[0]);
+    put_file(dir + "/.zattrs",
+             std::string("{\"multiscales\":[{\"version\":\"0.4\",\"name\":\"deconvolved\",\"axes\":["
+                         "{\"name\":\"z\",\"type\":\"space\",\"unit\":\"micrometer\"},{\"name\":\"y\",\"type\":\"space\",\"unit\":\"micrometer\"},"
+                         "{\"name\":\"x\",\"type\":\"space\",\"unit\":\"micrometer\"}],"
+                         "\"datasets\":[{\"path\":\"0\",\"coordinateTransformations\":[{\"type\":\"scale\",\"scale\":") + scale + "}]}]}]}");
+    std::string za = "{\"zarr_format\":2,\"shape\":[" + std::to_string(dims[2]) + "," + std::to_string(dims[1]) + "," + std::to_string(dims[0]) + "],\"chunks\":[" +
+                     std::to_string(chunk[2]) + "," + std::to_string(chunk[1]) + "," + std::to_string(chunk[0]) + "],\"dtype\":\"<f4\",\"order\":\"C\",\"fill_value\":0,"
+                     "\"dimension_separator\":\"/\",\"filters\":null,\"compressor\":";
+    za += gzip_level < 0 ? std::string("null}") : "{\"id\":\"gzip\",\"level\":" + std::to_string(gzip_level) + "}}";
+    put_file(arr + "/.zarray", za);
+    long long grid[3];
+    for (int i = 0; i < 3; ++i) grid[i] = ((long long)dims[i] + chunk[i] - 1) / chunk[i];
+    std::vector<float> buf((size_t)chunk[0] * chunk[1] * chunk[2]);
+    for (long long gz = 0; gz < grid[2]; ++gz)
+        for (long long gy = 0; gy < grid[1]; ++gy)
+            for (long long gx = 0; gx < grid[0]; ++gx) {
+                std::fill(buf.begin(), buf.end(), 0.f);
+                const long long x0 = gx * chunk[0], y0 = gy * chunk[1], z0 = gz * chunk[2];
+                const long long bx = std::min<long long>(chunk[0], dims[0] - x0);
+                for (long long z = 0; z < chunk[2] && z0 + z < dims[2]; ++z)
+                    for (long long y = 0; y < chunk[1] && y0 + y < dims[1]; ++y)
+                        std::memcpy(buf.data() + ((size_t)z * chunk[1] + y) * chunk[0], data + ((size_t)(z0 + z) * dims[1] + (y0 + y)) * dims[0] + x0,
+                                    sizeof(float) * (size_t)bx);                     // (x86 / CUDA hosts are little endian: "<f4" as stored)
+                const unsigned char* raw = reinterpret_cast<const unsigned char*>(buf.data());
+                const size_t nbytes = buf.size() * sizeof(float);
+                const std::string sub = arr + "/" + std::to_string(gz) + "/" + std::to_string(gy);
+                mkdirs(sub);
+                FILE* f = std::fopen((sub + "/" + std::to_string(gx)).c_str(), "wb");
+                if (!f) throw Error("Zarr: cannot write a chunk under " + sub);
+                size_t w, want;
+                if (gzip_level < 0) { want = nbytes; w = std::fwrite(raw, 1, nbytes, f); }
+                else { const std::vector<unsigned char> c = gzip_all(raw, nbytes, gzip_level); want = c.size(); w = std::fwrite(c.data(), 1, c.size(), f); }
+                std::fclose(f);
+                if (w != want) throw Error("Zarr: short write under " + sub);
+            }
+}
+
 }  // namespace mvd

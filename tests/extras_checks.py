@@ -411,3 +411,31 @@ def check_debug_interval(lib, oracle, small_dataset):
     assert res[0][1] == [] and res[1][1] == [0, 1, 2, 3] and res[2][1] == [1, 3]
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][0], res[2][0])
     assert np.array_equal(res[1][2][0], psi0) and np.array_equal(res[1][2][1], res[2][2][0])
+
+
+def check_zarr_export(lib, tmp_path):
+    """mvd_zarr_write: an OME-Zarr 0.4 group read back with nothing but json / gzip / numpy (Zarr v2 layout: full-size C-order
+    little-endian chunks, edge chunks padded with the fill value, "/" as dimension separator)."""
+    import gzip, json, os
+    rng = np.random.default_rng(13)
+    vol = rng.random((21, 19, 37), dtype=np.float32) * 50
+    for level in (1, -1):
+        root = os.path.join(str(tmp_path), f"out{level}.zarr")
+        lib.zarr_write(root, vol, (16, 8, 16), level, voxel_size_xyz=(0.5, 0.5, 2.0))
+        assert json.load(open(os.path.join(root, ".zgroup"))) == {"zarr_format": 2}
+        ms = json.load(open(os.path.join(root, ".zattrs")))["multiscales"][0]
+        assert ms["version"] == "0.4" and [a["name"] for a in ms["axes"]] == ["z", "y", "x"] and ms["datasets"][0]["path"] == "0"
+        assert ms["datasets"][0]["coordinateTransformations"][0] == {"type": "scale", "scale": [2.0, 0.5, 0.5]}
+        za = json.load(open(os.path.join(root, "0", ".zarray")))
+        assert za["shape"] == [21, 19, 37] and za["chunks"] == [16, 8, 16] and za["dtype"] == "<f4" and za["order"] == "C"
+        assert za["dimension_separator"] == "/" and za["fill_value"] == 0 and za["zarr_format"] == 2
+        assert za["compressor"] == (None if level < 0 else {"id": "gzip", "level": level})
+        back = np.zeros((32, 24, 48), dtype=np.float32)
+        for iz in range(2):
+            for iy in range(3):
+                for ix in range(3):
+                    raw = open(os.path.join(root, "0", str(iz), str(iy), str(ix)), "rb").read()
+                    if level >= 0:
+                        raw = gzip.decompress(raw)
+                    back[iz * 16:(iz + 1) * 16, iy * 8:(iy + 1) * 8, ix * 16:(ix + 1) * 16] = np.frombuffer(raw, dtype="<f4").reshape(16, 8, 16)
+        assert np.array_equal(back[:21, :19, :37], vol) and not back[21:].any() and not back[:, 19:].any() and not back[:, :, 37:].any()

@@ -51,3 +51,7 @@ def test_n5_io(product_lib, tmp_path):
 
 def test_debug_interval(product_lib, oracle, small_dataset):
     X.check_debug_interval(product_lib, oracle, small_dataset)
+
+
+def test_zarr_export(product_lib, tmp_path):
+    X.check_zarr_export(product_lib, tmp_path)

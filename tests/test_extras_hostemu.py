@@ -53,3 +53,7 @@ def test_n5_io(hostemu_lib, tmp_path):
 
 def test_debug_interval(hostemu_lib, oracle, small_dataset):
     X.check_debug_interval(hostemu_lib, oracle, small_dataset)
+
+
+def test_zarr_export(hostemu_lib, tmp_path):
+    X.check_zarr_export(hostemu_lib, tmp_path)
