@@ -185,6 +185,22 @@ def test_exchange_callback_and_two_exchange_scheme(hostemu_lib, oracle, tmp_path
     assert oracle.rel_l2(got, ref) < 4e-6
 
 
+def test_three_ranks_along_y_with_an_interior_rank(hostemu_lib, oracle, tmp_path):
+    """N = 4 on the GPU box is a 4 x 1 grid: ranks in the middle have a neighbour on both y sides, so the boundary-first quotient pass runs
+    with two interior sides and both z sides at volume faces.  Three gloo ranks reproduce that case."""
+    import torch.multiprocessing as mp
+    world, dims = 3, (40, 42, 24)
+    port = 32300 + (os.getpid() % 2000)
+    mp.start_processes(_worker_cb, args=(world, port, hostemu_lib.path, str(tmp_path), "y", 1, dims, 0), nprocs=world, join=True,
+                       start_method="spawn")
+    ds = oracle.make_synthetic(dims, VIEWS, seed=6, **KW_CB)
+    views, psi0, avg = oracle.make_oracle_views(ds, oracle.EFFICIENT_BAYESIAN)
+    ref, _ = oracle.run_iterations_seq(psi0, views, 2, 0.0, dtype=np.float64)
+    got = np.concatenate([np.load(tmp_path / f"part{r}.npy") for r in range(world)], axis=1)
+    assert got.shape == ref.shape
+    assert oracle.rel_l2(got, ref) < 4e-6
+
+
 def test_two_exchange_scheme_with_several_x_tiles(hostemu_lib, oracle, tmp_path):
     """exchange scheme 1 on a box that needs two FFT tiles along x (c4: 2048 + margins > one 2160-sample tile at equal cost): every tile
     exchanges its own quotient spectrum; y / z still fit one tile."""
