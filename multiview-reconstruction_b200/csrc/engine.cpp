@@ -271,6 +271,25 @@ void Convolver::xpass(int kind, XArgs a, int z0, int z1) {
     if (z1 < 0) z1 = T_[2];
     a.line0 = z0 * T_[1];
     a.line_end = z1 * T_[1];
+    // MVD_CHECK_RECTS=1 (tests): the rectangle list of a filtered launch must enumerate exactly the lines the box filter selects --
+    // the two forms are consumed by different kernel shapes and have to describe the same set
+    static const bool check_rects = [] { const char* e = std::getenv("MVD_CHECK_RECTS"); return e && std::atoi(e) != 0; }();
+    if (check_rects && a.nrect > 0) {
+        a.ty = T_[1];
+        std::vector<unsigned char> hit((size_t)T_[1] * T_[2], 0);
+        for (int r = 0; r < a.nrect; ++r) {
+            if (a.rect_start[r + 1] - a.rect_start[r] != (a.rect[r][1] - a.rect[r][0]) * (a.rect[r][3] - a.rect[r][2])) throw Error("internal: selection rectangle count");
+            for (int z = a.rect[r][2]; z < a.rect[r][3]; ++z)
+                for (int y = a.rect[r][0]; y < a.rect[r][1]; ++y) {
+                    if (y < 0 || y >= T_[1] || z < 0 || z >= T_[2] || hit[(size_t)z * T_[1] + y]) throw Error("internal: selection rectangles overlap or leave the tile");
+                    hit[(size_t)z * T_[1] + y] = 1;
+                }
+        }
+        for (int l = 0; l < T_[1] * T_[2]; ++l) {
+            const bool want = l >= a.line0 && x_line_selected(a, l);
+            if (want != (hit[(size_t)l] != 0)) throw Error("internal: selection rectangles and line filter disagree at line " + std::to_string(l));
+        }
+    }
     const int nb = (a.line_end - a.line0 + ox_->XL - 1) / ox_->XL;
     a.nblocks = nb;
     if (a.part_sum) { a.part_sum += (size_t)(a.line0 / ox_->XL) + (size_t)z0; a.part_max += (size_t)(a.line0 / ox_->XL) + (size_t)z0; }
@@ -460,7 +479,7 @@ void Convolver::view_update(const float* psi_in, float* psi_out, const float* im
             const bool deep = dy1 > dy0 && dz1 > dz0;
             a.src = img;                                  // P5: quotient, 1 where there is no image data
             a.fin[0] = ey0; a.fin[1] = ey1; a.fin[2] = q0; a.fin[3] = q1;
-            a.fkeep = 1;      // + the lines outside the volume (margins at volume faces): their quotient is 1, nobody delivers them
+            a.fkeep = 1;      // + all rows of the planes outside the volume in z (face margins): their quotient is 1, nobody delivers them
             if (deep) { a.fout[0] = dy0; a.fout[1] = dy1; a.fout[2] = dz0; a.fout[3] = dz1; }
             {
                 // the same selection as rectangles: (own box, extended at faces) minus the deep interior, plus the interior-side halo rows

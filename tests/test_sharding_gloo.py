@@ -120,6 +120,7 @@ KW_CB = dict(psf_size_xyz=(5, 5, 5), psf_sigma_xyz=(1.0, 1.1, 1.3), bead_density
 
 
 def _worker_cb(rank, world, port, lib_path, out_dir, axis, scheme, dims=None, max_len=0):
+    os.environ["MVD_CHECK_RECTS"] = "1"   # the rectangle form of every filtered x launch must equal its box-filter form
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch.distributed as dist
@@ -223,6 +224,7 @@ DIMS_2D = (40, 44, 24)
 
 def _worker_grid(rank, world, port, lib_path, out_dir, scheme):
     os.environ["MVD_SPLIT_P1"] = "1"      # also cover the (opt-in) split of the forward pass around the psi exchange
+    os.environ["MVD_CHECK_RECTS"] = "1"
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch.distributed as dist
